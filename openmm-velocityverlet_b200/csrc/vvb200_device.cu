@@ -1,0 +1,1763 @@
+// vvb200_device.cu -- hand-written sm_100a kernels + device-side plan state + C-ABI step calls.
+//
+// Design: the reference's 10-16 launches per step collapse
+// into two streaming passes over the particle arrays, both working on molecule-aligned tiles:
+//
+//   pass A  kick_reduce_kernel   velm += dt*w*(F + Fextra)   [integrateMiddleVel, middle.cu:6;
+//           extra forces computed inline: drudeLangevin.cu:2 (via the compact ldForce array),
+//           electricField.cu:2, cosineAccelerate.cu:2]; per-molecule COM velocity
+//           [calcCOMVelocities, drudeNoseHoover.cu:5] from shared memory in the reference's
+//           summation order; group kinetic energies of the COM-normalised velocities
+//           [normalizeVelocities :37 + computeNormalizedKineticEnergies :55] and the velocity-bias
+//           moments [calcPeriodicVelocityBias, cosineAccelerate.cu:16]; deterministic two-level
+//           reduction [replaces sumNormalizedKineticEnergies :121 and sumV :34]; the LAST block
+//           advances the Nose-Hoover chains on the device [VVIntegrator::propagateNHChain,
+//           VVIntegrator.cpp:340-376] -- no D2H/H2D round trip (CudaVVKernels.cpp:709-746).
+//   pass B  scale_drift_kernel   thermostat scaling [scaleVelocity, drudeNoseHoover.cu:157], bias
+//           remove/restore [cosineAccelerate.cu:63,76], both half drifts and the double-float
+//           position write [integrateMiddlePos1/2/3, middle.cu:29-100], Drude hard wall
+//           [applyHardWallConstraints, middle.cu:106].
+//
+// velm (mixed4 = 32 B in mixed/double mode) moves with single 256-bit LDG/STG instructions, a
+// Blackwell (sm_100) addition.  All sums are fp64 (`mixed`) in a fixed order: results are bitwise
+// reproducible run to run.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "vvb200_internal.h"
+
+#define BOLTZ_D (1.380649e-23 * 6.02214076e23 / 1000.0)
+#define AVOGADRO_D 6.02214076e23
+
+#define THREADS 256
+#define VVB200_MAX_BLOCKS_PER_SM 8
+#define ITEMS (VVB200_TILE_CAP / THREADS)
+static_assert(VVB200_TILE_CAP % THREADS == 0, "tile must be a multiple of the block");
+static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
+
+// ------------------------------------------------------------------------------------------------
+// precision traits: OpenMM's CudaPrecision modes
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(32) D4 { double x, y, z, w; };
+struct F3 { float x, y, z; };
+struct D3 { double x, y, z; };
+
+template <int MODE> struct Prec;
+template <> struct Prec<VVB200_SINGLE> {
+    typedef float real; typedef float mixed; typedef F4 real4; typedef F4 mixed4; typedef F3 real3;
+    static constexpr bool kMixed = false;
+};
+template <> struct Prec<VVB200_MIXED> {
+    typedef float real; typedef double mixed; typedef F4 real4; typedef D4 mixed4; typedef F3 real3;
+    static constexpr bool kMixed = true;
+};
+template <> struct Prec<VVB200_DOUBLE> {
+    typedef double real; typedef double mixed; typedef D4 real4; typedef D4 mixed4; typedef D3 real3;
+    static constexpr bool kMixed = false;
+};
+
+// SQRT / RECIP as OpenMM defines them for the JIT'ed kernels [OMM-mem]: sqrtf and 1.0f/(x) unless
+// CudaPrecision=double.  (1.0f/(double) is still a double division.)
+template <int MODE, class T> __device__ __forceinline__ T vv_sqrt(T x) {
+    if (MODE == VVB200_DOUBLE) return (T) sqrt((double) x);
+    return (T) sqrtf((float) x);
+}
+__device__ __forceinline__ float vv_recip(float x) { return 1.0f / x; }
+__device__ __forceinline__ double vv_recip(double x) { return 1.0 / x; }
+
+// ---- streaming loads / stores ------------------------------------------------------------------
+__device__ __forceinline__ D4 ld_stream(const D4 *p) {
+    D4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ F4 ld_stream(const F4 *p) {
+    F4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(D4 *p, const D4 &v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(F4 *p, const F4 &v) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ long long ld_force(const long long *p) {
+    long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident thermostat state
+// ------------------------------------------------------------------------------------------------
+struct NhcDevice {
+    double eta[3][VVB200_MAX_CHAINS];
+    double etaDot[3][VVB200_MAX_CHAINS + 1];
+    double etaDotDot[3][VVB200_MAX_CHAINS];
+    double etaMass[3][VVB200_MAX_CHAINS];
+    double NkbT[3];
+    double tTarget[3];
+    double ke2[3];
+    double vscale[3];
+    double red[VVB200_NRED];     // this rank's (or, after an all-reduce, the global) sums
+    double vBias;
+    double invMassTotal;
+    int numTG, nc, loops;
+};
+
+struct KParams {
+    int N, paddedN, numTiles;
+    const int32_t *tileStart, *tileMolOffset, *tileMolList, *tileMolInfo;
+    const uint32_t *slotMeta;
+    const int32_t *ldSlot;
+    const int32_t *sortedByMol, *particlesInMolecules;
+    void *posq, *corr, *velm;
+    const long long *force;
+    const void *ldForce;
+    void *comV;            // mixed4 per molecule
+    void *comCbar;         // mixed per molecule (cosine runs)
+    double *partials;      // [gridDim.x][NRED]
+    NhcDevice *nhc;
+    unsigned int *counter;
+    double dt;
+    double efscale, accel, invBoxZ, maxDrudeDistance, hardwallScale;
+    int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC;
+};
+
+enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
+enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2 };
+
+// tileMolInfo word: bits 0-10 first slot in tile, bits 11-21 count, bit 31 = not contiguous
+#define MOLINFO_FIRST(w) ((w) & 0x7FF)
+#define MOLINFO_COUNT(w) (((w) >> 11) & 0x7FF)
+#define MOLINFO_SCATTERED(w) (((w) >> 31) & 1)
+
+__device__ __forceinline__ double cosPhase(double z, double invBoxZ) {
+    // the reference's 8-digit pi literal and double-precision cos (cosineAccelerate.cu:9,26,70,83)
+    return cos(2 * 3.1415926 * z * invBoxZ);
+}
+
+// VVIntegrator::propagateNHChain on the device (VVIntegrator.cpp:340-376)
+__device__ double nhcPropagate(NhcDevice *s, int g, double dt, double ke2) {
+    const int nc = s->nc, loops = s->loops;
+    double *eta = s->eta[g], *etaDot = s->etaDot[g], *etaDotDot = s->etaDotDot[g];
+    const double *Q = s->etaMass[g];
+    const double target = s->NkbT[g];
+    const double h2 = dt / loops / 2, h4 = h2 / 2, h8 = h4 / 2;
+    double factor = 1.0, e = 0.0;
+    etaDotDot[0] = (ke2 - target) / Q[0];
+    for (int l = 0; l < loops; l++) {
+        for (int k = nc - 1; k >= 0; k--) {
+            e = exp(-h8 * etaDot[k + 1]);
+            etaDot[k] *= e;
+            etaDot[k] += etaDotDot[k] * h4;
+            etaDot[k] *= e;
+        }
+        factor *= exp(-h2 * etaDot[0]);
+        for (int k = 0; k < nc; k++)
+            eta[k] += h2 * etaDot[k];
+        etaDotDot[0] = (ke2 * factor * factor - target) / Q[0];
+        etaDot[0] *= e;
+        etaDot[0] += etaDotDot[0] * h4;
+        etaDot[0] *= e;
+        for (int k = 1; k < nc; k++) {
+            e = exp(-h8 * etaDot[k + 1]);
+            etaDot[k] *= e;
+            etaDotDot[k] = (Q[k - 1] * etaDot[k - 1] * etaDot[k - 1] - BOLTZ_D * s->tTarget[g]) / Q[k];
+            etaDot[k] += etaDotDot[k] * h4;
+            etaDot[k] *= e;
+        }
+    }
+    return factor;
+}
+
+// From the reduced sums to bias, group energies and scale factors (CudaVVKernels.cpp:709-746 moved
+// onto the device).  Called by threads 0..2 of one block; `red` must already be final.
+template <bool COS>
+__device__ void nhcFinish(NhcDevice *s, double dt, int g) {
+    const double *red = s->red;
+    double V = 0.0;
+    if (COS)
+        V = red[3] * s->invMassTotal;
+    double ke2 = red[g];
+    if (COS)
+        ke2 = red[g] - 2.0 * V * red[4 + g] + V * V * red[7 + g];
+    double scale = 1.0;
+    if (g < s->numTG) {
+        if (s->etaMass[g][0] > 0)
+            scale = nhcPropagate(s, g, dt, ke2);
+    } else {
+        ke2 = 0.0;
+    }
+    s->ke2[g] = ke2;
+    s->vscale[g] = scale;
+    if (g == 0)
+        s->vBias = V;
+}
+
+template <bool COS>
+__global__ void nhc_kernel(NhcDevice *s, double dt) {
+    if (threadIdx.x < 3)
+        nhcFinish<COS>(s, dt, threadIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass A
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool COS> struct SmemA {
+    typedef typename Prec<MODE>::mixed mixed;
+    mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], w[VVB200_TILE_CAP];
+    double cphase[COS ? VVB200_TILE_CAP : 1];   // cos(2*pi*z/Lz) is always evaluated in fp64
+    // per tile-local molecule: COM velocity and 1/M (and mass-weighted mean phase for COS)
+    mixed Vx[VVB200_TILE_CAP], Vy[VVB200_TILE_CAP], Vz[VVB200_TILE_CAP];
+    mixed cbar[COS ? VVB200_TILE_CAP : 1];
+    double red[THREADS / 32][VVB200_NRED];
+    unsigned int ticket;
+};
+
+template <int MODE, bool COS, int KICK>
+__global__ void __launch_bounds__(THREADS) kick_reduce_kernel(const KParams p) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SmemA<MODE, COS> &sm = *reinterpret_cast<SmemA<MODE, COS> *>(smemRaw);
+
+    const int tid = threadIdx.x;
+    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
+    const real4 *posq = reinterpret_cast<const real4 *>(p.posq);
+    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
+    mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
+    mixed *comCbar = reinterpret_cast<mixed *>(p.comCbar);
+
+    const mixed stepSize = (mixed) p.dt;
+    // middle.cu:11-12 / CudaVVKernels.cpp:306
+    const mixed fscale = KICK == KICK_VV ? (mixed) (0.5 * p.dt / (double) 0x100000000)
+                                         : stepSize / (mixed) 0x100000000;
+    const real efscale = (real) p.efscale;
+    const real accel = (real) p.accel;
+    const real invBoxZ = (real) p.invBoxZ;
+
+    // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
+    mixed acc[VVB200_NRED];
+#pragma unroll
+    for (int k = 0; k < VVB200_NRED; k++) acc[k] = 0;
+
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        const int t0 = p.tileStart[tile], t1 = p.tileStart[tile + 1];
+        const int m0 = p.tileMolOffset[tile], nMol = p.tileMolOffset[tile + 1] - m0;
+
+        mixed4 vel[ITEMS];
+        uint32_t meta[ITEMS];
+        // ---- phase 1: loads, extra forces, kick, stage --------------------------------------
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * THREADS + tid;
+            const int idx = t0 + loc;
+            const bool valid = idx < t1;
+            meta[it] = VVB200_META_MOL_NONE;
+            vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
+            double cph = 0;
+            if (valid) {
+                meta[it] = __ldg(p.slotMeta + idx);
+                mixed4 v = ld_stream(velm + idx);
+                if (COS)
+                    cph = cosPhase((double) posq[idx].z, (double) invBoxZ);
+                if (KICK != KICK_NONE && v.w != 0) {
+                    const long long fx = ld_force(p.force + idx);
+                    const long long fy = ld_force(p.force + idx + p.paddedN);
+                    const long long fz = ld_force(p.force + idx + 2 * (size_t) p.paddedN);
+                    // forceExtra as the reference builds it: reset, += Langevin, += field, += cosine
+                    real ex = 0, ey = 0, ez = 0;
+                    if (p.extraForces) {
+                        if (p.hasLD && (meta[it] & VVB200_META_LD)) {
+                            const real3 f = ldForce[p.ldSlot[idx]];
+                            ex = f.x; ey = f.y; ez = f.z;
+                        }
+                        if (p.hasField) {
+                            const int cnt = (meta[it] >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
+                            if (cnt) {
+                                const real q = posq[idx].w;
+                                for (int c = 0; c < cnt; c++)
+                                    ez += efscale * q;                         // electricField.cu:10
+                            }
+                        }
+                        if (COS)   // cosineAccelerate.cu:9 (float += double unless double mode)
+                            ex = (real) (ex + accel * cph * vv_recip(v.w));
+                    }
+                    if (KICK == KICK_MIDDLE) {   // middle.cu:17-19
+                        v.x += stepSize * v.w * ex + fscale * v.w * fx;
+                        v.y += stepSize * v.w * ey + fscale * v.w * fy;
+                        v.z += stepSize * v.w * ez + fscale * v.w * fz;
+                    } else {                      // velocityVerlet.cu:19-21 (0.5 is a double literal)
+                        v.x += 0.5 * stepSize * v.w * ex + fscale * v.w * fx;
+                        v.y += 0.5 * stepSize * v.w * ey + fscale * v.w * fy;
+                        v.z += 0.5 * stepSize * v.w * ez + fscale * v.w * fz;
+                    }
+                    st_stream(velm + idx, v);
+                }
+                vel[it] = v;
+                if (COS && v.w != 0)   // cosineAccelerate.cu:26
+                    acc[3] += vv_recip(v.w) * v.x * 2 * cph;
+            }
+            sm.vx[loc] = vel[it].x; sm.vy[loc] = vel[it].y; sm.vz[loc] = vel[it].z; sm.w[loc] = vel[it].w;
+            if (COS) sm.cphase[loc] = cph;
+        }
+        __syncthreads();
+
+        // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), one
+        //      thread per molecule, particles in ascending order like particlesSortedByMolId ----
+        if (p.useCOM) {
+            for (int j = tid; j < nMol; j += THREADS) {
+                const uint32_t info = (uint32_t) p.tileMolInfo[m0 + j];
+                const int mol = p.tileMolList[m0 + j];
+                mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
+                if (!MOLINFO_SCATTERED(info)) {
+                    const int first = MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
+                    for (int k = first; k < first + cnt; k++) {
+                        const mixed w = sm.w[k];
+                        if (w != 0) {
+                            const mixed mass = vv_recip(w);
+                            sx += sm.vx[k] * mass; sy += sm.vy[k] * mass; sz += sm.vz[k] * mass;
+                            if (COS) sc += sm.cphase[k] * mass;
+                            comMass += mass;
+                        }
+                    }
+                } else {
+                    const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
+                    for (int k = 0; k < cnt; k++) {
+                        const int loc = p.sortedByMol[start + k] - t0;
+                        if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
+                        const mixed w = sm.w[loc];
+                        if (w != 0) {
+                            const mixed mass = vv_recip(w);
+                            sx += sm.vx[loc] * mass; sy += sm.vy[loc] * mass; sz += sm.vz[loc] * mass;
+                            if (COS) sc += sm.cphase[loc] * mass;
+                            comMass += mass;
+                        }
+                    }
+                }
+                mixed4 V;
+                V.w = vv_recip(comMass);
+                V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
+                sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
+                st_stream(comV + mol, V);
+                mixed cb = 0;
+                if (COS) {
+                    cb = sc * V.w;
+                    sm.cbar[j] = cb;
+                    comCbar[mol] = cb;
+                }
+                // molecular temperature group (drudeNoseHoover.cu:91-97)
+                if (V.w != 0) {
+                    const mixed M = 1 / V.w;   // only used by the COS moments
+                    acc[1] += (V.x * V.x + V.y * V.y + V.z * V.z) / V.w;
+                    if (COS) {
+                        acc[5] += M * V.x * cb;
+                        acc[8] += M * cb * cb;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- phase 3: group kinetic energies of the COM-normalised velocities ------------------
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const uint32_t mw = meta[it];
+            if (!(mw & VVB200_META_NH)) continue;
+            const int loc = it * THREADS + tid;
+            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
+            const uint32_t lm = mw & VVB200_META_MOL_MASK;
+            mixed Vx = 0, Vy = 0, Vz = 0, cb = 0;
+            if (p.useCOM && lm != VVB200_META_MOL_NONE) {
+                Vx = sm.Vx[lm]; Vy = sm.Vy[lm]; Vz = sm.Vz[lm];
+                if (COS) cb = sm.cbar[lm];
+            }
+            const mixed4 v = vel[it];
+            if (role == VVB200_ROLE_NONE) {
+                if (v.w != 0) {   // drudeNoseHoover.cu:76-83
+                    const mixed ux = v.x - Vx, uy = v.y - Vy, uz = v.z - Vz;
+                    acc[0] += (ux * ux + uy * uy + uz * uz) / v.w;
+                    if (COS) {
+                        const mixed d = sm.cphase[loc] - cb;
+                        acc[4] += ux * d / v.w;
+                        acc[7] += d * d / v.w;
+                    }
+                }
+            } else if (role == VVB200_ROLE_DRUDE) {   // drudeNoseHoover.cu:99-114; this thread owns the pair
+                const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+                const mixed w1 = v.w, w2 = sm.w[ploc];
+                const mixed u1x = v.x - Vx, u1y = v.y - Vy, u1z = v.z - Vz;
+                const mixed u2x = sm.vx[ploc] - Vx, u2y = sm.vy[ploc] - Vy, u2z = sm.vz[ploc] - Vz;
+                const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
+                const mixed invTotalMass = vv_recip(mass1 + mass2);
+                const mixed invReducedMass = (mass1 + mass2) * w1 * w2;
+                const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
+                const mixed cmx = u1x * m1f + u2x * m2f, cmy = u1y * m1f + u2y * m2f, cmz = u1z * m1f + u2z * m2f;
+                const mixed rx = u1x - u2x, ry = u1y - u2y, rz = u1z - u2z;
+                acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * (mass1 + mass2);
+                acc[2] += (rx * rx + ry * ry + rz * rz) / invReducedMass;
+                if (COS) {
+                    const mixed d1 = sm.cphase[loc] - cb, d2 = sm.cphase[ploc] - cb;
+                    const mixed cmd = d1 * m1f + d2 * m2f, rd = d1 - d2;
+                    acc[4] += cmx * cmd * (mass1 + mass2);
+                    acc[7] += cmd * cmd * (mass1 + mass2);
+                    acc[6] += rx * rd / invReducedMass;
+                    acc[9] += rd * rd / invReducedMass;
+                }
+            }
+        }
+        __syncthreads();   // shared staging is reused by the next tile
+    }
+
+    // ---- block reduction (fixed order), then the last block finishes ----------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NR = COS ? VVB200_NRED : 3;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        double v = (double) acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm.red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < NR) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) v += sm.red[w][tid];
+        p.partials[(size_t) blockIdx.x * VVB200_NRED + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+        sm.ticket = atomicAdd(p.counter, 1u);
+    __syncthreads();
+    if (sm.ticket != gridDim.x - 1)
+        return;
+    // last block: sum the per-block partials block-major in a fixed order
+    __threadfence();
+    for (int k = 0; k < NR; k++) {
+        double v = 0;
+        for (int b = tid; b < (int) gridDim.x; b += THREADS)
+            v += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm.red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < VVB200_NRED) {
+        double v = 0;
+        if (tid < NR)
+            for (int w = 0; w < THREADS / 32; w++) v += sm.red[w][tid];
+        p.nhc->red[tid] = v;
+    }
+    if (tid == 0)
+        *p.counter = 0;
+    __syncthreads();
+    if (p.fuseNHC && tid < 3)
+        nhcFinish<COS>(p.nhc, p.dt, tid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool COS, bool POS> struct SmemB {
+    typedef typename Prec<MODE>::mixed mixed;
+    mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], w[VVB200_TILE_CAP];
+    mixed px[POS ? VVB200_TILE_CAP : 1], py[POS ? VVB200_TILE_CAP : 1], pz[POS ? VVB200_TILE_CAP : 1];
+    double cphase[COS ? VVB200_TILE_CAP : 1];
+    mixed Vx[VVB200_TILE_CAP], Vy[VVB200_TILE_CAP], Vz[VVB200_TILE_CAP];
+    mixed cbar[COS ? VVB200_TILE_CAP : 1];
+};
+
+// thermostat scaling of one particle given its partner (drudeNoseHoover.cu:164-208).  v* are
+// COM-normalised (and bias-free) velocities; returns the new absolute velocity of `self`.
+template <class mixed>
+__device__ __forceinline__ void scalePair(const mixed v1[3], mixed w1, const mixed v2[3], mixed w2, const mixed V[3],
+                                          mixed sA, mixed sC, mixed sD, mixed out1[3], mixed out2[3]) {
+    const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
+    const mixed invTotalMass = vv_recip(mass1 + mass2);
+    const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        mixed cm = v1[d] * m1f + v2[d] * m2f;
+        mixed rel = v2[d] - v1[d];
+        cm = sA * cm;
+        rel = sD * rel;
+        out1[d] = cm - rel * m2f + sC * V[d];
+        out2[d] = cm + rel * m1f + sC * V[d];
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void splitPos(typename Prec<MODE>::mixed x, typename Prec<MODE>::real &hi,
+                                         typename Prec<MODE>::real &lo) {
+    typedef typename Prec<MODE>::real real;
+    hi = (real) x;
+    lo = (real) (x - (typename Prec<MODE>::mixed) hi);
+}
+
+template <int MODE, bool COS, int VARIANT>
+__global__ void __launch_bounds__(THREADS) scale_drift_kernel(const KParams p) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    constexpr bool POS = VARIANT != VAR_SCALE_ONLY;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SmemB<MODE, COS, POS> &sm = *reinterpret_cast<SmemB<MODE, COS, POS> *>(smemRaw);
+
+    const int tid = threadIdx.x;
+    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
+    real4 *posq = reinterpret_cast<real4 *>(p.posq);
+    real4 *corr = reinterpret_cast<real4 *>(p.corr);
+    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
+    const mixed4 *comV = reinterpret_cast<const mixed4 *>(p.comV);
+    const mixed *comCbar = reinterpret_cast<const mixed *>(p.comCbar);
+
+    const mixed stepSize = (mixed) p.dt;
+    const mixed halfdt = 0.5f * stepSize;                       // middle.cu:33,51
+    const mixed invStepSize = (mixed) (1.0 / stepSize);         // velocityVerlet.cu:40
+    const mixed fscaleVV = (mixed) (0.5 * p.dt / (double) 0x100000000);
+    const mixed sA = (mixed) p.nhc->vscale[0], sC = (mixed) p.nhc->vscale[1], sD = (mixed) p.nhc->vscale[2];
+    const mixed Vb = COS ? (mixed) p.nhc->vBias : (mixed) 0;
+    const mixed maxD = (mixed) p.maxDrudeDistance;
+    const mixed hwScale = (mixed) p.hardwallScale;
+    const real efscale = (real) p.efscale;
+    const real accel = (real) p.accel;
+    const real invBoxZ = (real) p.invBoxZ;
+
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        const int t0 = p.tileStart[tile], t1 = p.tileStart[tile + 1];
+        const int m0 = p.tileMolOffset[tile], nMol = p.tileMolOffset[tile + 1] - m0;
+
+        mixed4 vel[ITEMS];
+        real4 pq[ITEMS];
+        mixed pos[ITEMS][3];
+        uint32_t meta[ITEMS];
+        double cph[ITEMS];
+        // ---- phase 1: load + stage ---------------------------------------------------------------
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * THREADS + tid;
+            const int idx = t0 + loc;
+            meta[it] = VVB200_META_MOL_NONE;
+            vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
+            pos[it][0] = pos[it][1] = pos[it][2] = 0;
+            cph[it] = 0;
+            if (idx < t1) {
+                meta[it] = __ldg(p.slotMeta + idx);
+                vel[it] = ld_stream(velm + idx);
+                if (POS || COS) {
+                    pq[it] = ld_stream(posq + idx);
+                    if (P::kMixed) {
+                        const real4 c = ld_stream(corr + idx);
+                        pos[it][0] = pq[it].x + (mixed) c.x;       // middle.cu:82-84
+                        pos[it][1] = pq[it].y + (mixed) c.y;
+                        pos[it][2] = pq[it].z + (mixed) c.z;
+                    } else {
+                        pos[it][0] = pq[it].x; pos[it][1] = pq[it].y; pos[it][2] = pq[it].z;
+                    }
+                    if (COS) cph[it] = cosPhase((double) pq[it].z, (double) invBoxZ);
+                }
+            }
+            sm.vx[loc] = vel[it].x; sm.vy[loc] = vel[it].y; sm.vz[loc] = vel[it].z; sm.w[loc] = vel[it].w;
+            if (POS) { sm.px[loc] = pos[it][0]; sm.py[loc] = pos[it][1]; sm.pz[loc] = pos[it][2]; }
+            if (COS) sm.cphase[loc] = cph[it];
+        }
+        if (p.useCOM) {
+            for (int j = tid; j < nMol; j += THREADS) {
+                const int mol = p.tileMolList[m0 + j];
+                const mixed4 V = comV[mol];
+                sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
+                if (COS) sm.cbar[j] = comCbar[mol];
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: per particle ------------------------------------------------------------------
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * THREADS + tid;
+            const int idx = t0 + loc;
+            if (idx >= t1) continue;
+            const uint32_t mw = meta[it];
+            const bool isNH = mw & VVB200_META_NH;
+            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
+            const uint32_t lm = mw & VVB200_META_MOL_MASK;
+            const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+            const bool hasMol = p.useCOM && lm != VVB200_META_MOL_NONE;
+            mixed V[3] = {0, 0, 0};
+            mixed cb = 0;
+            if (hasMol) {
+                V[0] = sm.Vx[lm]; V[1] = sm.Vy[lm]; V[2] = sm.Vz[lm];
+                if (COS) cb = sm.cbar[lm];
+            }
+            // this particle ("s") and, for pair roles, its partner ("q")
+            mixed vs[3] = {vel[it].x, vel[it].y, vel[it].z};
+            const mixed ws = vel[it].w;
+            mixed vq[3] = {0, 0, 0}, wq = 0;
+            double cq = 0;
+            if (role != VVB200_ROLE_NONE) {
+                vq[0] = sm.vx[ploc]; vq[1] = sm.vy[ploc]; vq[2] = sm.vz[ploc]; wq = sm.w[ploc];
+                if (COS) cq = sm.cphase[ploc];
+            }
+            // velocities entering the drift as "pre-thermostat" values (middle.cu:33-41)
+            const mixed vs0[3] = {vs[0], vs[1], vs[2]};
+            const mixed vq0[3] = {vq[0], vq[1], vq[2]};
+            bool writeVel = false;
+
+            if (isNH) {
+                // removePeriodicVelocityBias (all atoms; only matters for thermostatted ones here since
+                // remove and restore cancel exactly elsewhere -- they do not: see below)
+                if (COS) { vs[0] -= Vb * cph[it]; vq[0] -= Vb * cq; }
+                // bias-removed molecular velocity: V' = V - Vb*cbar e_x
+                mixed Vn[3] = {V[0], V[1], V[2]};
+                if (COS && hasMol) Vn[0] = V[0] - Vb * cb;
+                if (hasMol) {   // normalizeVelocities, drudeNoseHoover.cu:42-48
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { vs[d] -= Vn[d]; vq[d] -= Vn[d]; }
+                }
+                if (role == VVB200_ROLE_NONE) {
+                    if (ws != 0) {
+#pragma unroll
+                        for (int d = 0; d < 3; d++) vs[d] = sA * vs[d] + sC * Vn[d];   // drudeNoseHoover.cu:172-176
+                    }
+                    writeVel = COS || hasMol || ws != 0;
+                } else {
+                    mixed o1[3], o2[3];
+                    if (role == VVB200_ROLE_DRUDE) {
+                        scalePair<mixed>(vs, ws, vq, wq, Vn, sA, sC, sD, o1, o2);
+#pragma unroll
+                        for (int d = 0; d < 3; d++) { vs[d] = o1[d]; vq[d] = o2[d]; }
+                    } else {
+                        scalePair<mixed>(vq, wq, vs, ws, Vn, sA, sC, sD, o1, o2);
+#pragma unroll
+                        for (int d = 0; d < 3; d++) { vq[d] = o1[d]; vs[d] = o2[d]; }
+                    }
+                    writeVel = true;
+                }
+                if (COS) { vs[0] += Vb * cph[it]; vq[0] += Vb * cq; }   // restorePeriodicVelocityBias
+            } else if (COS) {
+                // non-thermostatted atoms still see remove then restore (cosineAccelerate.cu:63-84)
+                vs[0] -= Vb * cph[it]; vs[0] += Vb * cph[it];
+                vq[0] -= Vb * cq; vq[0] += Vb * cq;
+                writeVel = true;
+            }
+
+            if (VARIANT == VAR_SCALE_ONLY) {
+                if (writeVel) {
+                    mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                    st_stream(velm + idx, o);
+                }
+                continue;
+            }
+
+            mixed xs[3] = {pos[it][0], pos[it][1], pos[it][2]};
+            mixed xq[3] = {0, 0, 0};
+            if (role != VVB200_ROLE_NONE) { xq[0] = sm.px[ploc]; xq[1] = sm.py[ploc]; xq[2] = sm.pz[ploc]; }
+            bool writePos = false;
+
+            if (VARIANT == VAR_VV_FIRST) {
+                // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
+                // particle and (redundantly) its partner
+                for (int who = 0; who < 2; who++) {
+                    if (who == 1 && role == VVB200_ROLE_NONE) break;
+                    const int j = who == 0 ? idx : t0 + ploc;
+                    mixed *v = who == 0 ? vs : vq;
+                    const mixed w = who == 0 ? ws : wq;
+                    if (w == 0) continue;
+                    const uint32_t mj = who == 0 ? mw : __ldg(p.slotMeta + j);
+                    real ex = 0, ey = 0, ez = 0;
+                    if (p.extraForces) {
+                        if (p.hasLD && (mj & VVB200_META_LD)) {
+                            const real3 f = ldForce[p.ldSlot[j]];
+                            ex = f.x; ey = f.y; ez = f.z;
+                        }
+                        if (p.hasField) {
+                            const int cnt = (mj >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
+                            const real q = who == 0 ? pq[it].w : posq[j].w;
+                            for (int c = 0; c < cnt; c++) ez += efscale * q;
+                        }
+                        if (COS) {
+                            const double c = who == 0 ? cph[it] : cq;
+                            ex = (real) (ex + accel * c * vv_recip(w));
+                        }
+                    }
+                    const long long fx = ld_force(p.force + j);
+                    const long long fy = ld_force(p.force + j + p.paddedN);
+                    const long long fz = ld_force(p.force + j + 2 * (size_t) p.paddedN);
+                    v[0] += 0.5 * stepSize * w * ex + fscaleVV * w * fx;
+                    v[1] += 0.5 * stepSize * w * ey + fscaleVV * w * fy;
+                    v[2] += 0.5 * stepSize * w * ez + fscaleVV * w * fz;
+                }
+                // posDelta = dt*v ; x += posDelta ; v = posDelta/dt  (velocityVerlet.cu:25,52-58)
+                if (ws != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const mixed delta = stepSize * vs[d];
+                        xs[d] += delta;
+                        vs[d] = (mixed) (invStepSize * delta);
+                    }
+                    writePos = writeVel = true;
+                }
+                if (role != VVB200_ROLE_NONE && wq != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const mixed delta = stepSize * vq[d];
+                        xq[d] += delta;
+                        vq[d] = (mixed) (invStepSize * delta);
+                    }
+                }
+            } else {
+                // middle scheme without constraints: posDelta = oldDelta = halfdt*v0 + halfdt*v', so
+                // integrateMiddlePos3 leaves v' unchanged and moves x by posDelta (middle.cu:33-98)
+                if (ws != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        mixed delta = halfdt * vs0[d];
+                        delta += halfdt * vs[d];
+                        xs[d] += delta;
+                    }
+                    writePos = writeVel = true;
+                }
+                if (role != VVB200_ROLE_NONE && wq != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        mixed delta = halfdt * vq0[d];
+                        delta += halfdt * vq[d];
+                        xq[d] += delta;
+                    }
+                }
+            }
+
+            // ---- Drude hard wall (middle.cu:114-220), evaluated by both members of the pair ----------
+            if (p.hardwall && role != VVB200_ROLE_NONE) {
+                // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
+                if (P::kMixed) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        real hi, lo;
+                        if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
+                        if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
+                    }
+                } else if (MODE == VVB200_SINGLE) {
+                    // positions are already `real`
+                }
+                const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
+                mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
+                mixed *vel1 = selfIsDrude ? vs : vq, *vel2 = selfIsDrude ? vq : vs;
+                const mixed w1 = selfIsDrude ? ws : wq, w2 = selfIsDrude ? wq : ws;
+                const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
+                const mixed r = vv_sqrt<MODE, mixed>(dx * dx + dy * dy + dz * dz);
+                const mixed rInv = vv_recip(r);
+                if (rInv * maxD < 1) {
+                    const mixed bond[3] = {dx * rInv, dy * rInv, dz * rInv};
+                    const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
+                    const mixed deltaR = r - maxD;
+                    mixed deltaT = stepSize;
+                    mixed dotvr1 = vel1[0] * bond[0] + vel1[1] * bond[1] + vel1[2] * bond[2];
+                    mixed vp1[3];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) vp1[d] = vel1[d] - bond[d] * dotvr1;
+                    if (w2 == 0) {
+                        if (dotvr1 != 0) deltaT = deltaR / fabs(dotvr1);
+                        if (deltaT > stepSize) deltaT = stepSize;
+                        dotvr1 = -dotvr1 * hwScale / (fabs(dotvr1) * vv_sqrt<MODE, mixed>(mass1));
+                        const mixed dr = -deltaR + deltaT * dotvr1;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            pos1[d] += bond[d] * dr;
+                            vel1[d] = vp1[d] + bond[d] * dotvr1;
+                        }
+                    } else {
+                        const mixed invTotalMass = vv_recip(mass1 + mass2);
+                        mixed dotvr2 = vel2[0] * bond[0] + vel2[1] * bond[1] + vel2[2] * bond[2];
+                        mixed vp2[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) vp2[d] = vel2[d] - bond[d] * dotvr2;
+                        const mixed vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
+                        dotvr1 -= vbCMass;
+                        dotvr2 -= vbCMass;
+                        if (dotvr1 != dotvr2) deltaT = deltaR / fabs(dotvr1 - dotvr2);
+                        if (deltaT > stepSize) deltaT = stepSize;
+                        const mixed vBond = hwScale / vv_sqrt<MODE, mixed>(mass1);
+                        dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabs(dotvr1);
+                        dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabs(dotvr2);
+                        const mixed dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
+                        const mixed dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
+                        dotvr1 += vbCMass;
+                        dotvr2 += vbCMass;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            pos1[d] += bond[d] * dr1;
+                            pos2[d] += bond[d] * dr2;
+                            vel1[d] = vp1[d] + bond[d] * dotvr1;
+                            vel2[d] = vp2[d] + bond[d] * dotvr2;
+                        }
+                    }
+                    // the reference writes the touched members unconditionally (middle.cu:166-172, 204-219)
+                    if (selfIsDrude || w2 != 0) writePos = writeVel = true;
+                }
+            }
+
+            if (writeVel) {
+                mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                st_stream(velm + idx, o);
+            }
+            if (writePos) {
+                real4 o;
+                if (P::kMixed) {
+                    real4 oc;
+                    splitPos<MODE>(xs[0], o.x, oc.x);
+                    splitPos<MODE>(xs[1], o.y, oc.y);
+                    splitPos<MODE>(xs[2], o.z, oc.z);
+                    o.w = pq[it].w;
+                    oc.w = 0;
+                    st_stream(posq + idx, o);
+                    st_stream(corr + idx, oc);
+                } else {
+                    o.x = (real) xs[0]; o.y = (real) xs[1]; o.z = (real) xs[2]; o.w = pq[it].w;
+                    st_stream(posq + idx, o);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small gather kernels
+// ------------------------------------------------------------------------------------------------
+
+// Langevin force into the compact ldForce array (drudeLangevin.cu:2-59): value = what the reference
+// holds in forceExtra right after resetExtraForce + addExtraForceDrudeLangevin.
+template <int MODE>
+__global__ void langevin_force_kernel(const void *velmRaw, void *ldForceRaw, const int32_t *normalLD, int nNormal,
+                                      const int2 *pairsLD, int nPairs, double dragD, double randD, double dragDrudeD,
+                                      double randDrudeD, const float4 *random, unsigned int randomIndex) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    const mixed4 *velm = reinterpret_cast<const mixed4 *>(velmRaw);
+    real3 *out = reinterpret_cast<real3 *>(ldForceRaw);
+    const mixed dragFactor = (mixed) dragD, randFactor = (mixed) randD;
+    const mixed dragFactorDrude = (mixed) dragDrudeD, randFactorDrude = (mixed) randDrudeD;
+    const int stride = blockDim.x * gridDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nNormal; i += stride) {
+        const mixed4 v = velm[normalLD[i]];
+        real3 f; f.x = 0; f.y = 0; f.z = 0;
+        if (v.w != 0) {
+            const mixed mass = vv_recip(v.w);
+            const mixed sqrtMass = vv_sqrt<MODE, mixed>(mass);
+            const float4 r = random[randomIndex + i];
+            f.x += (-dragFactor * mass * v.x + randFactor * sqrtMass * r.x);
+            f.y += (-dragFactor * mass * v.y + randFactor * sqrtMass * r.y);
+            f.z += (-dragFactor * mass * v.z + randFactor * sqrtMass * r.z);
+        }
+        out[i] = f;
+    }
+    randomIndex += nNormal;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPairs; i += stride) {
+        const int2 pr = pairsLD[i];
+        const mixed4 v1 = velm[pr.x], v2 = velm[pr.y];
+        const mixed mass1 = vv_recip(v1.w), mass2 = vv_recip(v2.w);
+        const mixed totMass = mass1 + mass2;
+        const mixed sqrtTotMass = vv_sqrt<MODE, mixed>(totMass);
+        const mixed redMass = vv_recip((mass1 + mass2) * v1.w * v2.w);
+        const mixed sqrtRedMass = vv_sqrt<MODE, mixed>(redMass);
+        const mixed invTotMass = vv_recip(totMass);
+        const mixed m1f = invTotMass * mass1, m2f = invTotMass * mass2;
+        const float4 r1 = random[randomIndex + 2 * i], r2 = random[randomIndex + 2 * i + 1];
+        const mixed cm[3] = {v1.x * m1f + v2.x * m2f, v1.y * m1f + v2.y * m2f, v1.z * m1f + v2.z * m2f};
+        const mixed rel[3] = {v2.x - v1.x, v2.y - v1.y, v2.z - v1.z};
+        const float ra[3] = {r1.x, r1.y, r1.z}, rb[3] = {r2.x, r2.y, r2.z};
+        real a[3], b[3];
+        const real f1 = (real) m1f, f2 = (real) m2f;   // real3 * mixed resolves to operator*(real3, real)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const real cmForce = (real) (-dragFactor * totMass * cm[d] + randFactor * sqrtTotMass * ra[d]);
+            const real relForce = (real) (-dragFactorDrude * redMass * rel[d] + randFactorDrude * sqrtRedMass * rb[d]);
+            a[d] = (real) 0 + (f1 * cmForce - relForce);
+            b[d] = (real) 0 + (f2 * cmForce + relForce);
+        }
+        real3 fa, fb;
+        fa.x = a[0]; fa.y = a[1]; fa.z = a[2];
+        fb.x = b[0]; fb.y = b[1]; fb.z = b[2];
+        out[nNormal + 2 * i] = fa;
+        out[nNormal + 2 * i + 1] = fb;
+    }
+}
+
+// updateImagePositions (imageCharge.cu:2-27)
+template <int MODE>
+__global__ void image_kernel(void *posqRaw, void *corrRaw, const int2 *imagePairs, int nImages, double mirrorD) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    real4 *posq = reinterpret_cast<real4 *>(posqRaw);
+    real4 *corr = reinterpret_cast<real4 *>(corrRaw);
+    const mixed mirror = (mixed) mirrorD;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nImages; i += blockDim.x * gridDim.x) {
+        const int2 pr = imagePairs[i];
+        const real4 pp = posq[pr.y];
+        real4 pi = posq[pr.x];
+        pi.x = pp.x;
+        pi.y = pp.y;
+        if (P::kMixed) {
+            const real4 pc = corr[pr.y];
+            real4 ic = corr[pr.x];
+            ic.x = pc.x;
+            ic.y = pc.y;
+            mixed z = (mixed) pp.z + (mixed) pc.z;
+            z = mirror * 2 - z;
+            pi.z = (real) z;
+            ic.z = (real) (z - (real) z);
+            corr[pr.x] = ic;
+        } else {
+            pi.z = 2 * mirror - pp.z;
+        }
+        posq[pr.x] = pi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise kernels of the constraint-bearing path (OpenMM's constraint kernels run between them)
+// ------------------------------------------------------------------------------------------------
+
+// integrateMiddlePos1 / integrateMiddlePos2 (middle.cu:29-61)
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) delta_kernel(const void *velmRaw, void *posDeltaRaw, void *oldDeltaRaw, int N,
+                                                        double dt, int accumulate) {
+    typedef typename Prec<MODE>::mixed mixed;
+    typedef typename Prec<MODE>::mixed4 mixed4;
+    const mixed4 *velm = reinterpret_cast<const mixed4 *>(velmRaw);
+    mixed4 *posDelta = reinterpret_cast<mixed4 *>(posDeltaRaw);
+    mixed4 *oldDelta = reinterpret_cast<mixed4 *>(oldDeltaRaw);
+    const mixed halfdt = 0.5f * (mixed) dt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) {
+        const mixed4 v = ld_stream(velm + i);
+        if (v.w != 0) {
+            mixed4 d;
+            d.x = halfdt * v.x; d.y = halfdt * v.y; d.z = halfdt * v.z; d.w = 0;
+            if (accumulate) {
+                mixed4 a = ld_stream(posDelta + i), b = ld_stream(oldDelta + i);
+                a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+                b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+                st_stream(posDelta + i, a);
+                st_stream(oldDelta + i, b);
+            } else {
+                st_stream(posDelta + i, d);
+                st_stream(oldDelta + i, d);
+            }
+        }
+    }
+}
+
+// integrateMiddlePos3 (middle.cu:66-100)
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) finish_kernel(void *posqRaw, void *corrRaw, const void *posDeltaRaw,
+                                                         const void *oldDeltaRaw, void *velmRaw, int N, double dt) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    real4 *posq = reinterpret_cast<real4 *>(posqRaw);
+    real4 *corr = reinterpret_cast<real4 *>(corrRaw);
+    mixed4 *velm = reinterpret_cast<mixed4 *>(velmRaw);
+    const mixed4 *posDelta = reinterpret_cast<const mixed4 *>(posDeltaRaw);
+    const mixed4 *oldDelta = reinterpret_cast<const mixed4 *>(oldDeltaRaw);
+    const mixed invDt = 1 / (mixed) dt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) {
+        mixed4 v = ld_stream(velm + i);
+        if (v.w != 0) {
+            const mixed4 d = ld_stream(posDelta + i), o = ld_stream(oldDelta + i);
+            v.x += (d.x - o.x) * invDt;
+            v.y += (d.y - o.y) * invDt;
+            v.z += (d.z - o.z) * invDt;
+            st_stream(velm + i, v);
+            real4 pq = ld_stream(posq + i);
+            if (P::kMixed) {
+                const real4 c = ld_stream(corr + i);
+                mixed x = pq.x + (mixed) c.x, y = pq.y + (mixed) c.y, z = pq.z + (mixed) c.z;
+                x += d.x; y += d.y; z += d.z;
+                real4 oc;
+                splitPos<MODE>(x, pq.x, oc.x);
+                splitPos<MODE>(y, pq.y, oc.y);
+                splitPos<MODE>(z, pq.z, oc.z);
+                oc.w = 0;
+                st_stream(posq + i, pq);
+                st_stream(corr + i, oc);
+            } else {
+                pq.x += d.x; pq.y += d.y; pq.z += d.z;
+                st_stream(posq + i, pq);
+            }
+        }
+    }
+}
+
+// applyHardWallConstraints as a pair gather kernel (middle.cu:106-221), used after OpenMM's position
+// constraints where the fused pass B cannot be.
+template <int MODE>
+__global__ void hardwall_pairs_kernel(void *posqRaw, void *corrRaw, void *velmRaw, const int2 *pairs, int nPairs, double dt,
+                                      double maxDrudeDistance, double hardwallScale) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    real4 *posq = reinterpret_cast<real4 *>(posqRaw);
+    real4 *corr = reinterpret_cast<real4 *>(corrRaw);
+    mixed4 *velm = reinterpret_cast<mixed4 *>(velmRaw);
+    const mixed stepSize = (mixed) dt, maxD = (mixed) maxDrudeDistance, hwScale = (mixed) hardwallScale;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPairs; i += blockDim.x * gridDim.x) {
+        const int2 pr = pairs[i];
+        real4 q1 = posq[pr.x], q2 = posq[pr.y];
+        mixed pos1[3] = {(mixed) q1.x, (mixed) q1.y, (mixed) q1.z}, pos2[3] = {(mixed) q2.x, (mixed) q2.y, (mixed) q2.z};
+        if (P::kMixed) {
+            const real4 c1 = corr[pr.x], c2 = corr[pr.y];
+            pos1[0] += (mixed) c1.x; pos1[1] += (mixed) c1.y; pos1[2] += (mixed) c1.z;
+            pos2[0] += (mixed) c2.x; pos2[1] += (mixed) c2.y; pos2[2] += (mixed) c2.z;
+        }
+        const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
+        const mixed r = vv_sqrt<MODE, mixed>(dx * dx + dy * dy + dz * dz);
+        const mixed rInv = vv_recip(r);
+        if (!(rInv * maxD < 1))
+            continue;
+        const mixed bond[3] = {dx * rInv, dy * rInv, dz * rInv};
+        mixed4 v1 = velm[pr.x], v2 = velm[pr.y];
+        mixed vel1[3] = {v1.x, v1.y, v1.z}, vel2[3] = {v2.x, v2.y, v2.z};
+        const mixed mass1 = vv_recip(v1.w), mass2 = vv_recip(v2.w);
+        const mixed deltaR = r - maxD;
+        mixed deltaT = stepSize;
+        mixed dotvr1 = vel1[0] * bond[0] + vel1[1] * bond[1] + vel1[2] * bond[2];
+        mixed vp1[3];
+        for (int d = 0; d < 3; d++) vp1[d] = vel1[d] - bond[d] * dotvr1;
+        const bool both = v2.w != 0;
+        if (!both) {
+            if (dotvr1 != 0) deltaT = deltaR / fabs(dotvr1);
+            if (deltaT > stepSize) deltaT = stepSize;
+            dotvr1 = -dotvr1 * hwScale / (fabs(dotvr1) * vv_sqrt<MODE, mixed>(mass1));
+            const mixed dr = -deltaR + deltaT * dotvr1;
+            for (int d = 0; d < 3; d++) {
+                pos1[d] += bond[d] * dr;
+                vel1[d] = vp1[d] + bond[d] * dotvr1;
+            }
+        } else {
+            const mixed invTotalMass = vv_recip(mass1 + mass2);
+            mixed dotvr2 = vel2[0] * bond[0] + vel2[1] * bond[1] + vel2[2] * bond[2];
+            mixed vp2[3];
+            for (int d = 0; d < 3; d++) vp2[d] = vel2[d] - bond[d] * dotvr2;
+            const mixed vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
+            dotvr1 -= vbCMass;
+            dotvr2 -= vbCMass;
+            if (dotvr1 != dotvr2) deltaT = deltaR / fabs(dotvr1 - dotvr2);
+            if (deltaT > stepSize) deltaT = stepSize;
+            const mixed vBond = hwScale / vv_sqrt<MODE, mixed>(mass1);
+            dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabs(dotvr1);
+            dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabs(dotvr2);
+            const mixed dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
+            const mixed dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
+            dotvr1 += vbCMass;
+            dotvr2 += vbCMass;
+            for (int d = 0; d < 3; d++) {
+                pos1[d] += bond[d] * dr1;
+                pos2[d] += bond[d] * dr2;
+                vel1[d] = vp1[d] + bond[d] * dotvr1;
+                vel2[d] = vp2[d] + bond[d] * dotvr2;
+            }
+        }
+        for (int who = 0; who < (both ? 2 : 1); who++) {
+            const int idx = who == 0 ? pr.x : pr.y;
+            const mixed *x = who == 0 ? pos1 : pos2;
+            const mixed *v = who == 0 ? vel1 : vel2;
+            real4 o = who == 0 ? q1 : q2;
+            if (P::kMixed) {
+                real4 oc;
+                splitPos<MODE>(x[0], o.x, oc.x);
+                splitPos<MODE>(x[1], o.y, oc.y);
+                splitPos<MODE>(x[2], o.z, oc.z);
+                oc.w = 0;
+                posq[idx] = o;
+                corr[idx] = oc;
+            } else {
+                o.x = (real) x[0]; o.y = (real) x[1]; o.z = (real) x[2];
+                posq[idx] = o;
+            }
+            mixed4 ov;
+            ov.x = v[0]; ov.y = v[1]; ov.z = v[2]; ov.w = who == 0 ? v1.w : v2.w;
+            velm[idx] = ov;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: device state
+// ------------------------------------------------------------------------------------------------
+struct vvb200_device_state {
+    int device = 0;
+    int numSM = 148;
+    int numTiles = 0;
+    int32_t *tileStart = nullptr, *tileMolOffset = nullptr, *tileMolList = nullptr, *tileMolInfo = nullptr;
+    uint32_t *slotMeta = nullptr;
+    int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
+    int2 *pairsLD = nullptr, *imagePairs = nullptr, *drudePairs = nullptr;
+    void *oldDelta = nullptr;   // mixed4[N], plugin-owned like the reference's (CudaVVKernels.cpp:90-96)
+    void *comV = nullptr, *comCbar = nullptr, *ldForce = nullptr;
+    double *partials = nullptr;
+    NhcDevice *nhc = nullptr;
+    unsigned int *counter = nullptr;
+    bool extraForcesValid = false;   // VV scheme: forceExtra is zero until the first second half
+    // host staging for vvb200_step_host
+    void *hPosq = nullptr, *hCorr = nullptr, *hVelm = nullptr;
+    long long *hForce = nullptr;
+    size_t stagedN = 0;
+    std::vector<void *> allocations;
+};
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            vvb200_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return VVB200_ERR_CUDA;                                                               \
+        }                                                                                         \
+    } while (0)
+
+template <class T>
+static int uploadVec(vvb200_device_state *d, T **dst, const void *src, size_t count, cudaStream_t st) {
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc((void **) dst, bytes));
+    d->allocations.push_back(*dst);
+    CUDA_TRY(cudaMemsetAsync(*dst, 0, bytes, st));
+    if (count)
+        CUDA_TRY(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return VVB200_OK;
+}
+
+static size_t mixedSize(int precision) { return precision == VVB200_SINGLE ? 4 : 8; }
+static size_t realSize(int precision) { return precision == VVB200_DOUBLE ? 8 : 4; }
+
+extern "C" int vvb200_has_device_code(void) { return 1; }
+
+void vvb200_device_free(vvb200_plan *plan) {
+    vvb200_device_state *d = plan->dev;
+    if (!d)
+        return;
+    for (void *ptr : d->allocations)
+        cudaFree(ptr);
+    delete d;
+    plan->dev = nullptr;
+}
+
+static void fillNhcHost(const vvb200_plan *p, NhcDevice &h) {
+    memset(&h, 0, sizeof h);
+    const int nc = p->par.num_nh_chains;
+    h.numTG = p->numTempGroup;
+    h.nc = nc;
+    h.loops = p->par.loops_per_step;
+    const double realKbT = BOLTZ_D * p->par.temperature, drudeKbT = BOLTZ_D * p->par.drude_temperature;
+    for (int g = 0; g < 3; g++) {
+        h.vscale[g] = 1.0;
+        h.tTarget[g] = g == VVB200_TG_DRUDE ? p->par.drude_temperature : p->par.temperature;
+        if (g >= p->numTempGroup)
+            continue;
+        // same expressions as CudaVVKernels.cpp:583-594, on the (possibly global) DOFs
+        const double kT = g == VVB200_TG_DRUDE ? drudeKbT : realKbT;
+        const double q = g == VVB200_TG_DRUDE ? drudeKbT / std::pow(p->par.drude_frequency, 2)
+                                              : realKbT / std::pow(p->par.frequency, 2);
+        h.NkbT[g] = p->dofGlobal[g] * kT;
+        h.etaMass[g][0] = p->dofGlobal[g] * q;
+        for (int k = 1; k < nc; k++)
+            h.etaMass[g][k] = q;
+    }
+    h.invMassTotal = 1.0 / p->totalMassGlobal;
+}
+
+extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
+    if (!p) {
+        vvb200_set_error("vvb200_plan_upload: null plan");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    vvb200_device_free(p);
+    vvb200_device_state *d = new vvb200_device_state();
+    p->dev = d;
+    CUDA_TRY(cudaGetDevice(&d->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d->numSM, cudaDevAttrMultiProcessorCount, d->device));
+    if (!p->tiled) {
+        vvb200_set_error("vvb200_plan_upload: topology not supported by the tiled kernels (%s)", p->tiledWhyNot.c_str());
+        vvb200_device_free(p);
+        return VVB200_ERR_UNSUPPORTED_TOPOLOGY;
+    }
+    d->numTiles = (int) p->tileStart.size() - 1;
+
+    // per tile-local molecule: first slot, count, contiguity
+    std::vector<int32_t> molInfo(p->tileMolList.size(), 0);
+    {
+        std::vector<int32_t> first(p->M, -1), last(p->M, -1), cnt(p->M, 0);
+        for (int t = 0; t < d->numTiles; t++) {
+            const int a = p->tileStart[t], b = p->tileStart[t + 1];
+            for (int i = a; i < b; i++) {
+                const uint32_t lm = p->slotMeta[i] & VVB200_META_MOL_MASK;
+                if (lm == VVB200_META_MOL_NONE) continue;
+                const int m = p->particleMolId[i];
+                if (first[m] < 0) first[m] = i - a;
+                last[m] = i - a;
+                cnt[m]++;
+            }
+            for (int k = p->tileMolOffset[t]; k < p->tileMolOffset[t + 1]; k++) {
+                const int m = p->tileMolList[k];
+                uint32_t w = (uint32_t) first[m] | ((uint32_t) cnt[m] << 11);
+                if (last[m] - first[m] + 1 != cnt[m]) w |= 1u << 31;
+                molInfo[k] = (int32_t) w;
+                first[m] = last[m] = -1;
+                cnt[m] = 0;
+            }
+        }
+    }
+    int rc;
+    if ((rc = uploadVec(d, &d->tileStart, p->tileStart.data(), p->tileStart.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->tileMolOffset, p->tileMolOffset.data(), p->tileMolOffset.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->tileMolList, p->tileMolList.data(), p->tileMolList.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->tileMolInfo, molInfo.data(), molInfo.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->slotMeta, p->slotMeta.data(), p->slotMeta.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->sortedByMol, p->sortedByMol.data(), p->sortedByMol.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->particlesInMolecules, p->particlesInMolecules.data(), p->particlesInMolecules.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->ldSlot, p->ldSlot.data(), p->ldSlot.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->normalLD, p->normalLD.data(), p->normalLD.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->pairsLD, p->pairsLD.data(), p->pairsLD.size() / 2, st))) return rc;
+    if ((rc = uploadVec(d, &d->imagePairs, p->imagePairs.data(), p->imagePairs.size() / 2, st))) return rc;
+    if ((rc = uploadVec(d, &d->drudePairs, p->drudePairs.data(), p->drudePairs.size() / 2, st))) return rc;
+
+    const size_t ms = mixedSize(p->precision), rs = realSize(p->precision);
+    unsigned char *raw = nullptr;
+    if ((rc = uploadVec(d, &raw, nullptr, (size_t) p->M * 4 * ms, st))) return rc;   // zero-initialised, :606-617
+    d->comV = raw;
+    if ((rc = uploadVec(d, &raw, nullptr, (size_t) p->M * ms, st))) return rc;
+    d->comCbar = raw;
+    const size_t nLDslots = p->normalLD.size() + p->pairsLD.size();
+    if ((rc = uploadVec(d, &raw, nullptr, std::max<size_t>(nLDslots, 1) * 3 * rs, st))) return rc;
+    d->ldForce = raw;
+
+    // per-block partial sums: sized for the largest persistent grid any instantiation may use
+    if ((rc = uploadVec(d, &d->partials, nullptr, (size_t) d->numSM * VVB200_MAX_BLOCKS_PER_SM * VVB200_NRED, st))) return rc;
+    if ((rc = uploadVec(d, &d->counter, nullptr, 1, st))) return rc;
+    NhcDevice h;
+    fillNhcHost(p, h);
+    if ((rc = uploadVec(d, &d->nhc, &h, 1, st))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_set_global_thermostat(vvb200_plan *p, const double *dof3, double totalMass) {
+    if (!p || !dof3 || !(totalMass > 0)) {
+        vvb200_set_error("vvb200_set_global_thermostat: invalid argument");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    for (int g = 0; g < 3; g++) p->dofGlobal[g] = dof3[g];
+    p->totalMassGlobal = totalMass;
+    // temperature-group count follows the global DOFs (CudaVVKernels.cpp:567-573)
+    p->numTempGroup = 3;
+    if (p->dofGlobal[VVB200_TG_DRUDE] == 0) {
+        p->numTempGroup = 2;
+        if (p->dofGlobal[VVB200_TG_COM] == 0) p->numTempGroup = 1;
+    }
+    if (p->dev) {
+        NhcDevice h;
+        fillNhcHost(p, h);
+        CUDA_TRY(cudaMemcpy(p->dev->nhc, &h, sizeof h, cudaMemcpyHostToDevice));
+    }
+    return VVB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static int checkStepArgs(const vvb200_plan *p, const vvb200_buffers *b, const char *who, bool needPos, bool needForce) {
+    if (!p || !b) {
+        vvb200_set_error("%s: null argument", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!p->dev) {
+        vvb200_set_error("%s: plan not uploaded (call vvb200_plan_upload)", who);
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    if (!b->velm || (needPos && !b->posq) || (needForce && !b->force) ||
+        (needPos && p->precision == VVB200_MIXED && !b->posq_correction)) {
+        vvb200_set_error("%s: missing device buffer", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!p->particlesLD.empty() && needForce && !b->random) {
+        vvb200_set_error("%s: Langevin particles present but no random buffer", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if ((p->par.cos_acceleration != 0 || !p->particlesElectrolyte.empty()) && !b->posq) {
+        vvb200_set_error("%s: posq required", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    return VVB200_OK;
+}
+
+static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a) {
+    const vvb200_device_state *d = p->dev;
+    KParams k;
+    memset(&k, 0, sizeof k);
+    k.N = p->N; k.paddedN = p->paddedN; k.numTiles = d->numTiles;
+    k.tileStart = d->tileStart; k.tileMolOffset = d->tileMolOffset; k.tileMolList = d->tileMolList;
+    k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
+    k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
+    k.posq = b->posq; k.corr = b->posq_correction; k.velm = b->velm; k.force = b->force;
+    k.ldForce = d->ldForce; k.comV = d->comV; k.comCbar = d->comCbar;
+    k.partials = d->partials; k.nhc = d->nhc; k.counter = d->counter;
+    k.dt = p->par.step_size;
+    k.efscale = p->par.electric_field * AVOGADRO_D;          // CudaVVKernels.cpp:978
+    k.accel = p->par.cos_acceleration;                       // :1044
+    k.invBoxZ = a ? a->inv_box_z : 0.0;
+    k.maxDrudeDistance = p->par.max_drude_distance;          // :189
+    k.hardwallScale = std::sqrt(BOLTZ_D * p->par.drude_temperature);   // :190
+    k.useCOM = p->par.use_com_temp_group != 0 && !p->moleculesNH.empty();
+    k.hasLD = !p->particlesLD.empty();
+    k.hasField = !p->particlesElectrolyte.empty();
+    k.hardwall = p->par.max_drude_distance > 0 && !p->drudePairs.empty();
+    k.extraForces = 1;
+    k.fuseNHC = 1;
+    return k;
+}
+
+// Persistent launch geometry: one wave of co-resident blocks (148 SMs x blocks/SM from the occupancy
+// calculator), each striding over the molecule-aligned tiles.
+template <int MODE, bool COS, int KICK>
+static cudaError_t launchA(const KParams &k, int numSM, cudaStream_t st) {
+    const size_t smem = sizeof(SmemA<MODE, COS>);
+    static int perSM = 0;
+    if (!perSM) {
+        cudaFuncSetAttribute(kick_reduce_kernel<MODE, COS, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kick_reduce_kernel<MODE, COS, KICK>, THREADS, smem);
+        perSM = std::max(1, std::min(perSM, VVB200_MAX_BLOCKS_PER_SM));
+    }
+    const int grid = std::max(1, std::min(k.numTiles, numSM * perSM));
+    kick_reduce_kernel<MODE, COS, KICK><<<grid, THREADS, smem, st>>>(k);
+    return cudaGetLastError();
+}
+
+template <int MODE, bool COS, int VARIANT>
+static cudaError_t launchB(const KParams &k, int numSM, cudaStream_t st) {
+    const size_t smem = sizeof(SmemB<MODE, COS, VARIANT != VAR_SCALE_ONLY>);
+    static int perSM = 0;
+    if (!perSM) {
+        cudaFuncSetAttribute(scale_drift_kernel<MODE, COS, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, scale_drift_kernel<MODE, COS, VARIANT>, THREADS, smem);
+        perSM = std::max(1, std::min(perSM, VVB200_MAX_BLOCKS_PER_SM));
+    }
+    const int grid = std::max(1, std::min(k.numTiles, numSM * perSM));
+    scale_drift_kernel<MODE, COS, VARIANT><<<grid, THREADS, smem, st>>>(k);
+    return cudaGetLastError();
+}
+
+template <int KICK>
+static cudaError_t dispatchA(int precision, bool cosine, const KParams &k, int numSM, cudaStream_t st) {
+    switch (precision * 2 + (cosine ? 1 : 0)) {
+    case 0: return launchA<VVB200_SINGLE, false, KICK>(k, numSM, st);
+    case 1: return launchA<VVB200_SINGLE, true, KICK>(k, numSM, st);
+    case 2: return launchA<VVB200_MIXED, false, KICK>(k, numSM, st);
+    case 3: return launchA<VVB200_MIXED, true, KICK>(k, numSM, st);
+    case 4: return launchA<VVB200_DOUBLE, false, KICK>(k, numSM, st);
+    default: return launchA<VVB200_DOUBLE, true, KICK>(k, numSM, st);
+    }
+}
+
+template <int VARIANT>
+static cudaError_t dispatchB(int precision, bool cosine, const KParams &k, int numSM, cudaStream_t st) {
+    switch (precision * 2 + (cosine ? 1 : 0)) {
+    case 0: return launchB<VVB200_SINGLE, false, VARIANT>(k, numSM, st);
+    case 1: return launchB<VVB200_SINGLE, true, VARIANT>(k, numSM, st);
+    case 2: return launchB<VVB200_MIXED, false, VARIANT>(k, numSM, st);
+    case 3: return launchB<VVB200_MIXED, true, VARIANT>(k, numSM, st);
+    case 4: return launchB<VVB200_DOUBLE, false, VARIANT>(k, numSM, st);
+    default: return launchB<VVB200_DOUBLE, true, VARIANT>(k, numSM, st);
+    }
+}
+
+static int launchLangevin(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, cudaStream_t st) {
+    vvb200_device_state *d = p->dev;
+    const int nNormal = (int) p->normalLD.size(), nPairs = (int) p->pairsLD.size() / 2;
+    const int work = std::max(nNormal, nPairs);
+    if (work == 0)
+        return VVB200_OK;
+    // CudaVVKernels.cpp:835-839
+    const double dt = p->par.step_size;
+    const double drag = p->par.friction, dragDrude = p->par.drude_friction;
+    const double randF = std::sqrt(2.0 * BOLTZ_D * p->par.temperature * drag / dt);
+    const double randFD = std::sqrt(2.0 * BOLTZ_D * p->par.drude_temperature * dragDrude / dt);
+    const int grid = std::min((work + 127) / 128, d->numSM * 8);
+    const unsigned int ri = a ? a->random_index : 0;
+    switch (p->precision) {
+    case VVB200_SINGLE:
+        langevin_force_kernel<VVB200_SINGLE><<<grid, 128, 0, st>>>(b->velm, d->ldForce, d->normalLD, nNormal, d->pairsLD, nPairs,
+                                                                  drag, randF, dragDrude, randFD, (const float4 *) b->random, ri);
+        break;
+    case VVB200_MIXED:
+        langevin_force_kernel<VVB200_MIXED><<<grid, 128, 0, st>>>(b->velm, d->ldForce, d->normalLD, nNormal, d->pairsLD, nPairs,
+                                                                 drag, randF, dragDrude, randFD, (const float4 *) b->random, ri);
+        break;
+    default:
+        langevin_force_kernel<VVB200_DOUBLE><<<grid, 128, 0, st>>>(b->velm, d->ldForce, d->normalLD, nNormal, d->pairsLD, nPairs,
+                                                                  drag, randF, dragDrude, randFD, (const float4 *) b->random, ri);
+    }
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_update_image_positions(vvb200_plan *p, const vvb200_buffers *b, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_update_image_positions", true, false);
+    if (rc) return rc;
+    const int n = (int) p->imagePairs.size() / 2;
+    if (n == 0)
+        return VVB200_OK;
+    cudaStream_t st = (cudaStream_t) stream;
+    const int grid = std::min((n + 127) / 128, p->dev->numSM * 8);
+    switch (p->precision) {
+    case VVB200_SINGLE: image_kernel<VVB200_SINGLE><<<grid, 128, 0, st>>>(b->posq, b->posq_correction, p->dev->imagePairs, n, p->par.mirror_location); break;
+    case VVB200_MIXED: image_kernel<VVB200_MIXED><<<grid, 128, 0, st>>>(b->posq, b->posq_correction, p->dev->imagePairs, n, p->par.mirror_location); break;
+    default: image_kernel<VVB200_DOUBLE><<<grid, 128, 0, st>>>(b->posq, b->posq_correction, p->dev->imagePairs, n, p->par.mirror_location);
+    }
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+static bool hasNH(const vvb200_plan *p) { return !p->particlesNH.empty(); }
+
+extern "C" int vvb200_middle_kick_reduce(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_middle_kick_reduce", false, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+    KParams k = makeParams(p, b, a);
+    k.fuseNHC = 0;
+    CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, p->par.cos_acceleration != 0, k, p->dev->numSM, st)));
+    p->launches++;
+    return VVB200_OK;
+}
+
+static int launchNhc(vvb200_plan *p, cudaStream_t st) {
+    if (p->par.cos_acceleration != 0)
+        nhc_kernel<true><<<1, 32, 0, st>>>(p->dev->nhc, p->par.step_size);
+    else
+        nhc_kernel<false><<<1, 32, 0, st>>>(p->dev->nhc, p->par.step_size);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_middle_nhc_scale_drift", true, false);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (hasNH(p) && (rc = launchNhc(p, st))) return rc;
+    KParams k = makeParams(p, b, a);
+    CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, p->par.cos_acceleration != 0, k, p->dev->numSM, st)));
+    p->launches++;
+    return vvb200_update_image_positions(p, b, stream);
+}
+
+extern "C" int vvb200_partials_ptr(vvb200_plan *p, void **ptr, int32_t *n) {
+    if (!p || !p->dev || !ptr || !n) {
+        vvb200_set_error("vvb200_partials_ptr: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    *ptr = p->dev->nhc->red;   // address arithmetic only; never dereferenced on the host
+    *n = VVB200_NRED;
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_step_middle", true, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool cosine = p->par.cos_acceleration != 0;
+    if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+    KParams k = makeParams(p, b, a);
+    k.fuseNHC = hasNH(p);
+    CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    return vvb200_update_image_positions(p, b, stream);
+}
+
+extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_step_vv_first", true, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool cosine = p->par.cos_acceleration != 0;
+    KParams k = makeParams(p, b, a);
+    k.extraForces = p->dev->extraForcesValid ? 1 : 0;
+    if (hasNH(p)) {
+        CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
+        p->launches++;
+    }
+    CUDA_TRY((dispatchB<VAR_VV_FIRST>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    return vvb200_update_image_positions(p, b, stream);
+}
+
+extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_step_vv_second", true, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool cosine = p->par.cos_acceleration != 0;
+    if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+    p->dev->extraForcesValid = true;
+    KParams k = makeParams(p, b, a);
+    k.fuseNHC = hasNH(p);
+    CUDA_TRY((dispatchA<KICK_VV>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    if (hasNH(p)) {
+        CUDA_TRY((dispatchB<VAR_SCALE_ONLY>(p->precision, cosine, k, p->dev->numSM, st)));
+        p->launches++;
+    }
+    return VVB200_OK;
+}
+
+// ---- the VVKernels.h interfaces one by one (constraint-bearing path) ----------------------------
+extern "C" int vvb200_middle_kick(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    // extra forces + integrateMiddleVel; the reductions that ride along are discarded because OpenMM's
+    // applyVelocityConstraints runs next (CudaVVKernels.cpp:144-151)
+    return vvb200_middle_kick_reduce(p, b, a, stream);
+}
+
+extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_thermostat", false, false);
+    if (rc) return rc;
+    if (!hasNH(p))
+        return VVB200_OK;
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool cosine = p->par.cos_acceleration != 0;
+    KParams k = makeParams(p, b, a);
+    CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    CUDA_TRY((dispatchB<VAR_SCALE_ONLY>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    return VVB200_OK;
+}
+
+static int elementwiseGrid(const vvb200_plan *p, int n) {
+    return std::max(1, std::min((n + THREADS - 1) / THREADS, p->dev->numSM * 8));
+}
+
+extern "C" int vvb200_middle_delta(vvb200_plan *p, const vvb200_buffers *b, int accumulate, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_middle_delta", false, false);
+    if (rc) return rc;
+    if (!b->pos_delta) {
+        vvb200_set_error("vvb200_middle_delta: pos_delta buffer required");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    vvb200_device_state *d = p->dev;
+    if (!d->oldDelta) {
+        CUDA_TRY(cudaMalloc(&d->oldDelta, (size_t) p->paddedN * 4 * mixedSize(p->precision)));
+        d->allocations.push_back(d->oldDelta);
+        CUDA_TRY(cudaMemsetAsync(d->oldDelta, 0, (size_t) p->paddedN * 4 * mixedSize(p->precision), st));
+    }
+    const int grid = elementwiseGrid(p, p->N);
+    switch (p->precision) {
+    case VVB200_SINGLE: delta_kernel<VVB200_SINGLE><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, d->oldDelta, p->N, p->par.step_size, accumulate); break;
+    case VVB200_MIXED: delta_kernel<VVB200_MIXED><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, d->oldDelta, p->N, p->par.step_size, accumulate); break;
+    default: delta_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, d->oldDelta, p->N, p->par.step_size, accumulate);
+    }
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_middle_finish", true, false);
+    if (rc) return rc;
+    vvb200_device_state *d = p->dev;
+    if (!b->pos_delta || !d->oldDelta) {
+        vvb200_set_error("vvb200_middle_finish: pos_delta missing or vvb200_middle_delta not called yet");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    const int grid = elementwiseGrid(p, p->N);
+    const int nPairs = (int) p->drudePairs.size() / 2;
+    const bool hw = p->par.max_drude_distance > 0 && nPairs > 0;
+    const int gridHW = std::max(1, std::min((nPairs + 127) / 128, d->numSM * 8));
+    const double hwScale = std::sqrt(BOLTZ_D * p->par.drude_temperature);
+    switch (p->precision) {
+    case VVB200_SINGLE:
+        finish_kernel<VVB200_SINGLE><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, d->oldDelta, b->velm, p->N, p->par.step_size);
+        if (hw) hardwall_pairs_kernel<VVB200_SINGLE><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
+        break;
+    case VVB200_MIXED:
+        finish_kernel<VVB200_MIXED><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, d->oldDelta, b->velm, p->N, p->par.step_size);
+        if (hw) hardwall_pairs_kernel<VVB200_MIXED><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
+        break;
+    default:
+        finish_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, d->oldDelta, b->velm, p->N, p->par.step_size);
+        if (hw) hardwall_pairs_kernel<VVB200_DOUBLE><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
+    }
+    p->launches += hw ? 2 : 1;
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+// ---- state ------------------------------------------------------------------------------------
+extern "C" int vvb200_get_thermostat_state(vvb200_plan *p, vvb200_thermostat_state *out, void *stream) {
+    if (!p || !p->dev || !out) {
+        vvb200_set_error("vvb200_get_thermostat_state: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    NhcDevice h;
+    CUDA_TRY(cudaMemcpyAsync(&h, p->dev->nhc, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof *out);
+    const int nc = p->par.num_nh_chains;
+    out->num_temp_groups = p->numTempGroup;
+    out->velocity_bias = h.vBias;
+    for (int g = 0; g < 3; g++) {
+        out->ke2[g] = h.ke2[g];
+        out->vscale[g] = h.vscale[g];
+    }
+    for (int g = 0; g < p->numTempGroup; g++) {
+        for (int k = 0; k < nc; k++) {
+            out->eta[g * nc + k] = h.eta[g][k];
+            out->eta_dotdot[g * nc + k] = h.etaDotDot[g][k];
+        }
+        for (int k = 0; k < nc + 1; k++)
+            out->eta_dot[g * (nc + 1) + k] = h.etaDot[g][k];
+    }
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_set_thermostat_state(vvb200_plan *p, const vvb200_thermostat_state *in, void *stream) {
+    if (!p || !p->dev || !in) {
+        vvb200_set_error("vvb200_set_thermostat_state: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    NhcDevice h;
+    CUDA_TRY(cudaMemcpyAsync(&h, p->dev->nhc, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int nc = p->par.num_nh_chains;
+    for (int g = 0; g < p->numTempGroup; g++) {
+        for (int k = 0; k < nc; k++) {
+            h.eta[g][k] = in->eta[g * nc + k];
+            h.etaDotDot[g][k] = in->eta_dotdot[g * nc + k];
+        }
+        for (int k = 0; k < nc + 1; k++)
+            h.etaDot[g][k] = in->eta_dot[g * (nc + 1) + k];
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->dev->nhc, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_calc_viscosity(vvb200_plan *p, double bx, double by, double bz, double *vMax, double *invVis,
+                                     void *stream) {
+    if (!p || !p->dev || !vMax || !invVis) {
+        vvb200_set_error("vvb200_calc_viscosity: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    double v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, &p->dev->nhc->vBias, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (p->precision == VVB200_SINGLE)
+        v = (double) (float) v;
+    *vMax = v;
+    // CudaVVKernels.cpp:1129-1133
+    const double vol = bx * by * bz;
+    *invVis = v * vol * (1.0 / p->totalMassGlobal) / p->par.cos_acceleration * (2 * 3.1415926 / bz) * (2 * 3.1415926 / bz);
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_get_com_velocities(vvb200_plan *p, void *hostOut, void *stream) {
+    if (!p || !p->dev || !hostOut) {
+        vvb200_set_error("vvb200_get_com_velocities: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    CUDA_TRY(cudaMemcpyAsync(hostOut, p->dev->comV, (size_t) p->M * 4 * mixedSize(p->precision), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VVB200_OK;
+}
+
+// ---- host-buffer entry point ---------------------------------------------------------------------
+extern "C" int vvb200_step_host(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, int steps, void *stream) {
+    if (!p || !hb || steps < 0) {
+        vvb200_set_error("vvb200_step_host: invalid argument");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!p->dev) {
+        vvb200_set_error("vvb200_step_host: plan not uploaded (call vvb200_plan_upload)");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    if (!p->particlesLD.empty()) {
+        vvb200_set_error("vvb200_step_host: Langevin systems need the device random buffer; use the device entry points");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    vvb200_device_state *d = p->dev;
+    const size_t P = p->paddedN;
+    const size_t ms = mixedSize(p->precision), rs = realSize(p->precision);
+    if (d->stagedN != P) {
+        CUDA_TRY(cudaMalloc(&d->hPosq, P * 4 * rs)); d->allocations.push_back(d->hPosq);
+        CUDA_TRY(cudaMalloc(&d->hCorr, P * 4 * rs)); d->allocations.push_back(d->hCorr);
+        CUDA_TRY(cudaMalloc(&d->hVelm, P * 4 * ms)); d->allocations.push_back(d->hVelm);
+        CUDA_TRY(cudaMalloc((void **) &d->hForce, P * 3 * sizeof(long long))); d->allocations.push_back(d->hForce);
+        d->stagedN = P;
+    }
+    const bool mixedMode = p->precision == VVB200_MIXED;
+    CUDA_TRY(cudaMemcpyAsync(d->hVelm, hb->velm, P * 4 * ms, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->hForce, hb->force, P * 3 * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->hPosq, hb->posq, P * 4 * rs, cudaMemcpyHostToDevice, st));
+    if (mixedMode)
+        CUDA_TRY(cudaMemcpyAsync(d->hCorr, hb->posq_correction, P * 4 * rs, cudaMemcpyHostToDevice, st));
+    vvb200_buffers db;
+    memset(&db, 0, sizeof db);
+    db.posq = d->hPosq;
+    db.posq_correction = mixedMode ? d->hCorr : nullptr;
+    db.velm = d->hVelm;
+    db.force = d->hForce;
+    for (int s = 0; s < steps; s++) {
+        int rc;
+        if (p->par.use_middle_scheme) {
+            if ((rc = vvb200_step_middle(p, &db, a, stream))) return rc;
+        } else {
+            if ((rc = vvb200_step_vv_first(p, &db, a, stream))) return rc;
+            if ((rc = vvb200_step_vv_second(p, &db, a, stream))) return rc;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(hb->posq, d->hPosq, P * 4 * rs, cudaMemcpyDeviceToHost, st));
+    if (mixedMode)
+        CUDA_TRY(cudaMemcpyAsync(hb->posq_correction, d->hCorr, P * 4 * rs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hb->velm, d->hVelm, P * 4 * ms, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VVB200_OK;
+}

@@ -1,0 +1,87 @@
+// vvb200_internal.h -- plan object shared by the host builders (vvb200_plan.cpp) and the CUDA
+// side (vvb200_device.cu).  Not part of the public ABI (include/vvb200.h is).
+#ifndef VVB200_INTERNAL_H_
+#define VVB200_INTERNAL_H_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "vvb200.h"
+
+// ---- packed per-slot topology word read by the fused kernels -------------------------------
+//  bits  0-10  tile-local index of the particle's thermostat molecule (0x7FF = takes no part in
+//              a molecular centre of mass)
+//  bits 11-13  how many times the particle appears in the electrolyte list (duplicates add twice,
+//              CudaVVKernels.cpp:954-957 / electricField.cu:7-11)
+//  bit  16     member of the Nose-Hoover set (VVIntegrator::isParticleNH)
+//  bits 17-18  Drude pair role: 0 none, 1 Drude (pair.x), 2 parent (pair.y)
+//  bit  19     Langevin particle (has an entry in ldSlot[])
+//  bits 20-31  partner slot minus own slot, biased by 2048 (pair roles only)
+#define VVB200_META_MOL_MASK 0x7FFu
+#define VVB200_META_MOL_NONE 0x7FFu
+#define VVB200_META_ELEC_SHIFT 11
+#define VVB200_META_ELEC_MASK 0x7u
+#define VVB200_META_NH (1u << 16)
+#define VVB200_META_ROLE_SHIFT 17
+#define VVB200_META_ROLE_MASK 0x3u
+#define VVB200_META_LD (1u << 19)
+#define VVB200_META_PARTNER_SHIFT 20
+#define VVB200_META_PARTNER_BIAS 2048
+#define VVB200_ROLE_NONE 0u
+#define VVB200_ROLE_DRUDE 1u
+#define VVB200_ROLE_PARENT 2u
+
+// particles per tile of the fused kernels (threads x items); must be <= 1024 (11-bit local ids)
+#define VVB200_TILE_CAP 512
+
+// reduction vector layout (fp64), per block partial and final:
+//  [0..2]  A_g : sum m u^2 per temperature group (u = velocity relative to molecule COM, bias-free)
+//  [3]     S   : sum 2 m vx c          (cosine runs)   -> V = S / M_total
+//  [4..6]  B_g : first moment of the bias in group g   (cosine runs)
+//  [7..9]  C_g : second moment of the bias in group g  (cosine runs)
+#define VVB200_NRED 10
+
+struct vvb200_device_state;   // defined in vvb200_device.cu
+
+struct vvb200_plan {
+    int precision = VVB200_MIXED;
+    vvb200_params par{};
+    int N = 0, paddedN = 0, M = 0;
+    bool hasCMMotionRemover = false;
+
+    std::vector<double> masses;
+    // VVIntegrator members
+    std::vector<int32_t> particleMolId, particlesNH, moleculesNH, particlesLD, particlesElectrolyte;
+    std::vector<int32_t> imagePairs;            // flattened (image,parent)
+    std::vector<double> moleculeMasses, moleculeInvMasses;
+    // kernel-object arrays
+    std::vector<int32_t> drudePairs;            // flattened (p,p1)
+    std::vector<int32_t> sortedByMol, particlesInMolecules /* (count,start) */;
+    std::vector<int32_t> normalNH, pairsNH /* flattened */, normalLD, pairsLD /* flattened */;
+    double dof[3] = {0, 0, 0};
+    int numTempGroup = 1;
+    std::vector<double> etaMass, NkbT;          // [numTG*nc], [numTG]
+    double invMassTotal = 0;
+    // global-thermostat overrides for molecule-partitioned multi-GPU runs
+    double dofGlobal[3] = {0, 0, 0};
+    double totalMassGlobal = 0;
+
+    // fused-path tables
+    bool tiled = false;
+    std::string tiledWhyNot;
+    std::vector<int32_t> tileStart;             // [numTiles+1]
+    std::vector<int32_t> tileMolOffset;         // [numTiles+1] prefix into tileMolList
+    std::vector<int32_t> tileMolList;           // global molecule id of each tile-local molecule
+    std::vector<uint32_t> slotMeta;             // [N]
+    std::vector<int32_t> ldSlot;                // [N] compact Langevin-force slot or -1 (only if LD)
+    std::vector<unsigned char> isNH, isLD, isImage;
+
+    int64_t launches = 0;
+    vvb200_device_state *dev = nullptr;
+};
+
+void vvb200_set_error(const char *fmt, ...);
+void vvb200_device_free(vvb200_plan *plan);
+
+#endif

@@ -1,0 +1,332 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes wrappers for the CPU oracle (oracle/vv_oracle.c) and for
+the reference's own kernels compiled under oracle/_ref (oracle/ref_harness.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product (openmm-velocityverlet_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MODES = ("single", "mixed", "double")
+
+ARR = {"particlesNH": 0, "moleculesNH": 1, "particleMolId": 2, "drudePairs": 3, "sortedByMol": 4,
+       "particlesInMolecules": 5, "normalNH": 6, "pairsNH": 7, "normalLD": 8, "pairsLD": 9,
+       "imagePairs": 10, "electrolyte": 11,
+       "moleculeMasses": 100, "moleculeInvMasses": 101, "dof": 102, "etaMass": 103, "NkbT": 104,
+       "invMassTotal": 105, "eta": 106, "etaDot": 107, "etaDotDot": 108, "ke2": 109, "vscale": 110,
+       "vBias": 111}
+
+
+def build(target="all"):
+    """make -C oracle <target>; `ref` is a no-op when /root/reference is absent."""
+    subprocess.run(["make", "-s", "-C", HERE, target], check=True)
+
+
+class _System(C.Structure):
+    _fields_ = [("numParticles", C.c_int32), ("paddedNumAtoms", C.c_int32), ("numMolecules", C.c_int32),
+                ("masses", C.c_void_p), ("particleMolId", C.c_void_p),
+                ("numDrude", C.c_int32), ("drudePairs", C.c_void_p),
+                ("numConstraints", C.c_int32), ("constraints", C.c_void_p),
+                ("hasCMMotionRemover", C.c_int32),
+                ("numLD", C.c_int32), ("particlesLD", C.c_void_p),
+                ("numImagePairs", C.c_int32), ("imagePairs", C.c_void_p),
+                ("numElectrolyte", C.c_int32), ("particlesElectrolyte", C.c_void_p)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("temperature", C.c_double), ("frequency", C.c_double), ("drudeTemperature", C.c_double),
+                ("drudeFrequency", C.c_double), ("stepSize", C.c_double),
+                ("numNHChains", C.c_int32), ("loopsPerStep", C.c_int32),
+                ("useCOMTempGroup", C.c_int32), ("useMiddleScheme", C.c_int32),
+                ("maxDrudeDistance", C.c_double), ("friction", C.c_double), ("drudeFriction", C.c_double),
+                ("mirrorLocation", C.c_double), ("electricField", C.c_double), ("cosAcceleration", C.c_double)]
+
+
+class _Buffers(C.Structure):
+    _fields_ = [("posq", C.c_void_p), ("posqCorrection", C.c_void_p), ("velm", C.c_void_p),
+                ("force", C.c_void_p), ("posDelta", C.c_void_p), ("random", C.c_void_p)]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def _params_c(p):
+    return _Params(p.temperature, p.frequency, p.drude_temperature, p.drude_frequency, p.step_size,
+                   p.num_nh_chains, p.loops_per_step, int(p.use_com_temp_group), int(p.use_middle_scheme),
+                   p.max_drude_distance, p.friction, p.drude_friction, p.mirror_location, p.electric_field,
+                   p.cos_acceleration)
+
+
+_oracle_libs = {}
+
+
+def oracle_lib(mode):
+    if mode not in _oracle_libs:
+        path = os.path.join(HERE, "build", f"libvvoracle_{mode}.so")
+        if not os.path.exists(path):
+            build("oracle")
+        lib = C.CDLL(path)
+        lib.vvo_last_error.restype = C.c_char_p
+        lib.vvo_create.restype = C.c_void_p
+        lib.vvo_create.argtypes = [C.POINTER(_System), C.POINTER(_Params), C.c_int]
+        lib.vvo_destroy.argtypes = [C.c_void_p]
+        lib.vvo_num_temp_groups.argtypes = [C.c_void_p]
+        lib.vvo_get_array.restype = C.c_int64
+        lib.vvo_get_array.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.vvo_set_nhc_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vvo_find_molecules.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.vvo_propagate_nh_chain.argtypes = [C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+        lib.vvo_step.argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_int, C.c_double, C.POINTER(C.c_uint)]
+        for name in ("vvo_reset_extra_force",):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        for name in ("vvo_electric_force", "vvo_middle_vel", "vvo_middle_pos1", "vvo_middle_pos2", "vvo_middle_pos3",
+                     "vvo_hard_wall", "vvo_vv_positions", "vvo_scale_velocity", "vvo_update_images"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(_Buffers)]
+        lib.vvo_langevin_force.argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_uint]
+        lib.vvo_vv_velocities.argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_int]
+        for name in ("vvo_cosine_force", "vvo_calc_velocity_bias", "vvo_remove_velocity_bias", "vvo_restore_velocity_bias"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_double]
+        lib.vvo_calc_viscosity.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.vvo_toy_forces.argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_void_p, C.c_double, C.c_double]
+        lib.vvo_set_num_threads.argtypes = [C.c_int]
+        _oracle_libs[mode] = lib
+    return _oracle_libs[mode]
+
+
+def find_molecules(n, bonds):
+    lib = oracle_lib("mixed")
+    bonds = np.ascontiguousarray(bonds, dtype=np.int32).reshape(-1, 2)
+    out = np.empty(n, dtype=np.int32)
+    count = lib.vvo_find_molecules(n, bonds.shape[0], _ptr(bonds), _ptr(out))
+    return out, count
+
+
+def propagate_nh_chain(step_size, loops, eta, eta_dot, eta_dotdot, eta_mass, ke2, ke2_target, t_target):
+    lib = oracle_lib("mixed")
+    f = C.c_double()
+    lib.vvo_propagate_nh_chain(step_size, loops, len(eta), _ptr(eta), _ptr(eta_dot), _ptr(eta_dotdot), _ptr(eta_mass),
+                               ke2, ke2_target, t_target, C.byref(f))
+    return f.value
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _bufs(state, pos_delta=None):
+    return _Buffers(_ptr(state.posq), _ptr(state.corr) if state.corr is not None else None, _ptr(state.velm),
+                    _ptr(state.force), _ptr(pos_delta) if pos_delta is not None else None, _ptr(state.random))
+
+
+class Oracle:
+    """CPU restatement of the reference path for one system (oracle/vv_oracle.c)."""
+
+    def __init__(self, spec, params, precision="mixed", literal=True, threads=1):
+        self.lib = oracle_lib(precision)
+        self.lib.vvo_set_num_threads(threads)
+        self.spec, self.params, self.precision = spec, params, precision
+        self._keep = spec.c_arrays()
+        k = self._keep
+        s = _System(spec.n, spec.padded_n, spec.n_mol, _ptr(k["masses"]), _ptr(k["mol_id"]),
+                    spec.drude_pairs.shape[0], _ptr(k["drude_pairs"]), spec.constraints.shape[0], _ptr(k["constraints"]),
+                    int(spec.has_cmm), spec.langevin.shape[0], _ptr(k["langevin"]),
+                    spec.image_pairs.shape[0], _ptr(k["image_pairs"]), spec.electrolyte.shape[0], _ptr(k["electrolyte"]))
+        p = _params_c(params)
+        self.h = self.lib.vvo_create(C.byref(s), C.byref(p), int(literal))
+        if not self.h:
+            raise OracleError(self.lib.vvo_last_error().decode())
+        self.random_index = C.c_uint(0)
+        self._pos_delta = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.vvo_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def array(self, name):
+        p = C.c_void_p()
+        n = self.lib.vvo_get_array(self.h, ARR[name], C.byref(p))
+        if n < 0:
+            raise KeyError(name)
+        if n == 0:
+            return np.zeros(0, dtype=np.int32 if ARR[name] < 100 else np.float64)
+        ct = C.c_int32 if ARR[name] < 100 else C.c_double
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n,)).copy()
+
+    @property
+    def num_temp_groups(self):
+        return self.lib.vvo_num_temp_groups(self.h)
+
+    def _b(self, state):
+        if self._pos_delta is None or self._pos_delta.shape != state.velm.shape or self._pos_delta.dtype != state.velm.dtype:
+            self._pos_delta = np.zeros_like(state.velm)
+        return _bufs(state, self._pos_delta)
+
+    def step(self, state, steps=1, inv_box_z=0.0):
+        """advance `state` (HostState, in place) by whole integrator steps with frozen forces"""
+        b = self._b(state)
+        self.lib.vvo_step(self.h, C.byref(b), steps, inv_box_z, C.byref(self.random_index))
+
+    def scale_velocity(self, state):
+        b = self._b(state)
+        self.lib.vvo_scale_velocity(self.h, C.byref(b))
+
+    def call(self, kernel, state, *extra):
+        b = self._b(state)
+        getattr(self.lib, "vvo_" + kernel)(self.h, C.byref(b), *extra)
+
+    def toy_forces(self, state, x0, k_tether, k_drude):
+        b = self._b(state)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.lib.vvo_toy_forces(self.h, C.byref(b), _ptr(x0), k_tether, k_drude)
+
+    def thermostat_state(self):
+        ng, nc = self.num_temp_groups, self.params.num_nh_chains
+        return {"num_temp_groups": ng, "ke2": self.array("ke2"), "vscale": self.array("vscale"),
+                "velocity_bias": float(self.array("vBias")[0]),
+                "eta": self.array("eta").reshape(ng, nc), "eta_dot": self.array("etaDot").reshape(ng, nc + 1),
+                "eta_dotdot": self.array("etaDotDot").reshape(ng, nc)}
+
+    def viscosity(self, box):
+        v, iv = C.c_double(), C.c_double()
+        self.lib.vvo_calc_viscosity(self.h, box[0], box[1], box[2], C.byref(v), C.byref(iv))
+        return v.value, iv.value
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own kernels (oracle/_ref)
+# ---------------------------------------------------------------------------------------------
+class _RefIndices(C.Structure):
+    _fields_ = [("numAtoms", C.c_int32), ("paddedNumAtoms", C.c_int32), ("numMolecules", C.c_int32),
+                ("numDrude", C.c_int32), ("drudePairs", C.c_void_p),
+                ("numParticlesNH", C.c_int32), ("particlesNH", C.c_void_p),
+                ("numMoleculesNH", C.c_int32), ("moleculesNH", C.c_void_p),
+                ("numNormalNH", C.c_int32), ("normalParticlesNH", C.c_void_p),
+                ("numPairsNH", C.c_int32), ("pairParticlesNH", C.c_void_p),
+                ("particleMolId", C.c_void_p), ("particlesInMolecules", C.c_void_p),
+                ("particlesSortedByMolId", C.c_void_p),
+                ("numTempGroup", C.c_int32), ("etaMass", C.c_void_p), ("tempGroupNkbT", C.c_void_p),
+                ("numParticlesLD", C.c_int32),
+                ("numNormalLD", C.c_int32), ("normalParticlesLD", C.c_void_p),
+                ("numPairsLD", C.c_int32), ("pairParticlesLD", C.c_void_p),
+                ("numImagePairs", C.c_int32), ("imagePairs", C.c_void_p),
+                ("numElectrolyte", C.c_int32), ("particlesElectrolyte", C.c_void_p),
+                ("invMassTotal", C.c_double)]
+
+
+def ref_lib_path(mode, gpu=False):
+    return os.path.join(HERE, "_ref", f"libvvref_{'cuda' if gpu else 'cpu'}_{mode}.so")
+
+
+def ref_available(mode="mixed", gpu=False):
+    return os.path.exists(ref_lib_path(mode, gpu))
+
+
+_ref_libs = {}
+
+
+def ref_lib(mode, gpu=False):
+    key = (mode, gpu)
+    if key not in _ref_libs:
+        lib = C.CDLL(ref_lib_path(mode, gpu))
+        lib.vvref_create.restype = C.c_void_p
+        lib.vvref_create.argtypes = [C.POINTER(_RefIndices), C.POINTER(_Params), C.c_int, C.c_void_p]
+        lib.vvref_destroy.argtypes = [C.c_void_p]
+        lib.vvref_step.restype = C.c_long
+        lib.vvref_step.argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_int, C.c_double, C.POINTER(C.c_uint)]
+        lib.vvref_scale_velocity.argtypes = [C.c_void_p, C.POINTER(_Buffers)]
+        lib.vvref_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(C.c_double)]
+        lib.vvref_get_com_velm.argtypes = [C.c_void_p, C.c_void_p]
+        lib.vvref_set_num_threads.argtypes = [C.c_int]
+        _ref_libs[key] = lib
+    return _ref_libs[key]
+
+
+class Reference:
+    """The reference plugin's own kernels + restated host schedule (oracle/ref_harness.cpp).
+    `indices` come from an Oracle (or any object with .array(name)) built for the same system.
+    gpu=False: host build (SIMT shim). gpu=True: sm_100a build, buffers are device pointers."""
+
+    def __init__(self, oracle, gpu=False, num_thread_blocks=4 * 148, threads=1, stream=0):
+        spec, params = oracle.spec, oracle.params
+        self.precision = oracle.precision
+        self.gpu = gpu
+        self.lib = ref_lib(self.precision, gpu)
+        self.lib.vvref_set_num_threads(threads)
+        self.params = params
+        names = ("drudePairs", "particlesNH", "moleculesNH", "normalNH", "pairsNH", "particleMolId",
+                 "particlesInMolecules", "sortedByMol", "normalLD", "pairsLD", "imagePairs", "electrolyte",
+                 "etaMass", "NkbT")
+        a = self._keep = {k: np.ascontiguousarray(oracle.array(k)) for k in names}
+        self.num_temp_groups = oracle.num_temp_groups
+        ix = _RefIndices(spec.n, spec.padded_n, spec.n_mol,
+                         a["drudePairs"].size // 2, _ptr(a["drudePairs"]),
+                         a["particlesNH"].size, _ptr(a["particlesNH"]),
+                         a["moleculesNH"].size, _ptr(a["moleculesNH"]),
+                         a["normalNH"].size, _ptr(a["normalNH"]),
+                         a["pairsNH"].size // 2, _ptr(a["pairsNH"]),
+                         _ptr(a["particleMolId"]), _ptr(a["particlesInMolecules"]), _ptr(a["sortedByMol"]),
+                         self.num_temp_groups, _ptr(a["etaMass"]), _ptr(a["NkbT"]),
+                         spec.langevin.size,
+                         a["normalLD"].size, _ptr(a["normalLD"]), a["pairsLD"].size // 2, _ptr(a["pairsLD"]),
+                         a["imagePairs"].size // 2, _ptr(a["imagePairs"]),
+                         a["electrolyte"].size, _ptr(a["electrolyte"]),
+                         float(oracle.array("invMassTotal")[0]))
+        p = _params_c(params)
+        self.h = self.lib.vvref_create(C.byref(ix), C.byref(p), num_thread_blocks, C.c_void_p(stream))
+        self.random_index = C.c_uint(0)
+        self._pos_delta = None
+        self.n_mol = spec.n_mol
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.vvref_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _b_host(self, state):
+        if self._pos_delta is None or self._pos_delta.shape != state.velm.shape or self._pos_delta.dtype != state.velm.dtype:
+            self._pos_delta = np.zeros_like(state.velm)
+        return _bufs(state, self._pos_delta)
+
+    def _b_dev(self, bufs):
+        import torch
+        if self._pos_delta is None:
+            self._pos_delta = torch.zeros_like(bufs.velm)
+        p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None
+        return _Buffers(p(bufs.posq), p(bufs.corr), p(bufs.velm), p(bufs.force), p(self._pos_delta), p(bufs.random))
+
+    def step(self, state_or_bufs, steps=1, inv_box_z=0.0):
+        b = self._b_dev(state_or_bufs) if self.gpu else self._b_host(state_or_bufs)
+        return self.lib.vvref_step(self.h, C.byref(b), steps, inv_box_z, C.byref(self.random_index))
+
+    def scale_velocity(self, state_or_bufs):
+        b = self._b_dev(state_or_bufs) if self.gpu else self._b_host(state_or_bufs)
+        self.lib.vvref_scale_velocity(self.h, C.byref(b))
+
+    def thermostat_state(self):
+        ng, nc = self.num_temp_groups, self.params.num_nh_chains
+        ke2, vs = np.zeros(3), np.zeros(3)
+        eta, ed, edd = np.zeros(3 * nc), np.zeros(3 * (nc + 1)), np.zeros(3 * nc)
+        vb = C.c_double()
+        self.lib.vvref_get_state(self.h, _ptr(ke2), _ptr(vs), _ptr(eta), _ptr(ed), _ptr(edd), C.byref(vb))
+        return {"num_temp_groups": ng, "ke2": ke2[:ng], "vscale": vs[:ng], "velocity_bias": vb.value,
+                "eta": eta[: ng * nc].reshape(ng, nc), "eta_dot": ed[: ng * (nc + 1)].reshape(ng, nc + 1),
+                "eta_dotdot": edd[: ng * nc].reshape(ng, nc)}
+
+    def com_velm(self):
+        mixed = np.float32 if self.precision == "single" else np.float64
+        out = np.zeros((self.n_mol, 4), dtype=mixed)
+        self.lib.vvref_get_com_velm(self.h, _ptr(out))
+        return out
