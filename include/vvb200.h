@@ -230,6 +230,13 @@ int vvb200_get_com_velocities(vvb200_plan *plan, void *host_out, void *stream);
 /* kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 int64_t vvb200_launch_count(const vvb200_plan *plan);
 
+/* Optional per-kernel timing of the middle step for bench.py's roofline: CUDA events are recorded on
+ * the launching stream around pass A (kick + reductions) and pass B (scale + drift + position write) for
+ * up to max_steps steps (0 disables).  vvb200_profile_read synchronises on the last event, returns the
+ * summed durations in milliseconds and the number of steps they cover, and restarts the sampling. */
+int vvb200_profile_enable(vvb200_plan *plan, int max_steps);
+int vvb200_profile_read(vvb200_plan *plan, double *ms_pass_a, double *ms_pass_b, int32_t *steps);
+
 /* ---- host-buffer convenience (what Context.setPositions/setVelocities + step + getState do):
  * H2D of posq/posqCorrection/velm/force, `steps` integrator steps with those forces held
  * fixed, D2H of posq/posqCorrection/velm.  Pointers are HOST memory (pinned for full speed).

@@ -152,6 +152,8 @@ def load_library(path=None):
     lib.vvb200_launch_count.argtypes = [vp]
     lib.vvb200_launch_count.restype = i64
     lib.vvb200_step_host.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, vp]
+    lib.vvb200_profile_enable.argtypes = [vp, C.c_int]
+    lib.vvb200_profile_read.argtypes = [vp, P(dbl), P(dbl), P(i32)]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -360,6 +362,15 @@ class Plan:
         out = np.zeros((self.spec.n_mol, 4), dtype=mixed)
         _check(self.lib, self.lib.vvb200_get_com_velocities(self.h, _ptr(out), self._stream(stream)))
         return out
+
+    def profile_enable(self, max_steps):
+        _check(self.lib, self.lib.vvb200_profile_enable(self.h, int(max_steps)))
+
+    def profile_read(self):
+        """(ms in pass A, ms in pass B, steps covered) since the last read"""
+        a, b, n = C.c_double(), C.c_double(), C.c_int32()
+        _check(self.lib, self.lib.vvb200_profile_read(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def step_host(self, host_state, steps=1, inv_box_z=0.0, stream=None):
         """vvb200_step_host: host arrays in, host arrays out (H2D + steps + D2H inside)."""

@@ -1129,6 +1129,10 @@ struct vvb200_device_state {
     NhcDevice *nhc = nullptr;
     unsigned int *counter = nullptr;
     bool extraForcesValid = false;   // VV scheme: forceExtra is zero until the first second half
+    // optional per-kernel timing (vvb200_profile_*): events recorded on the launching stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> profEvents;      // 4 per step: before/after pass A, before/after pass B
+    size_t profUsed = 0;
     // host staging for vvb200_step_host
     void *hPosq = nullptr, *hCorr = nullptr, *hVelm = nullptr;
     long long *hForce = nullptr;
@@ -1151,7 +1155,7 @@ static int uploadVec(vvb200_device_state *d, T **dst, const void *src, size_t co
     CUDA_TRY(cudaMalloc((void **) dst, bytes));
     d->allocations.push_back(*dst);
     CUDA_TRY(cudaMemsetAsync(*dst, 0, bytes, st));
-    if (count)
+    if (count && src)
         CUDA_TRY(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
     return VVB200_OK;
 }
@@ -1167,6 +1171,8 @@ void vvb200_device_free(vvb200_plan *plan) {
         return;
     for (void *ptr : d->allocations)
         cudaFree(ptr);
+    for (cudaEvent_t e : d->profEvents)
+        cudaEventDestroy(e);
     delete d;
     plan->dev = nullptr;
 }
@@ -1451,6 +1457,59 @@ extern "C" int vvb200_update_image_positions(vvb200_plan *p, const vvb200_buffer
 
 static bool hasNH(const vvb200_plan *p) { return !p->particlesNH.empty(); }
 
+// per-kernel timing: which = 0 before pass A, 1 after it, 2 before pass B, 3 after it
+static void profMark(vvb200_device_state *d, int which, cudaStream_t st) {
+    if (!d->profiling)
+        return;
+    if (which == 0) {
+        if (d->profUsed + 4 > d->profEvents.size())
+            return;   // all slots used: later steps are not sampled
+    } else if (d->profUsed % 4 != (size_t) which) {
+        return;
+    }
+    cudaEventRecord(d->profEvents[d->profUsed++], st);
+}
+
+extern "C" int vvb200_profile_enable(vvb200_plan *p, int maxSteps) {
+    if (!p || !p->dev || maxSteps < 0) {
+        vvb200_set_error("vvb200_profile_enable: plan not uploaded or invalid argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    vvb200_device_state *d = p->dev;
+    while (d->profEvents.size() < (size_t) maxSteps * 4) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        d->profEvents.push_back(e);
+    }
+    d->profUsed = 0;
+    d->profiling = maxSteps > 0;
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_profile_read(vvb200_plan *p, double *msPassA, double *msPassB, int32_t *steps) {
+    if (!p || !p->dev || !msPassA || !msPassB || !steps) {
+        vvb200_set_error("vvb200_profile_read: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    vvb200_device_state *d = p->dev;
+    const size_t n = d->profUsed / 4;
+    double a = 0, b = 0;
+    if (n)
+        CUDA_TRY(cudaEventSynchronize(d->profEvents[4 * n - 1]));
+    for (size_t i = 0; i < n; i++) {
+        float ta = 0, tb = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ta, d->profEvents[4 * i], d->profEvents[4 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&tb, d->profEvents[4 * i + 2], d->profEvents[4 * i + 3]));
+        a += ta;
+        b += tb;
+    }
+    *msPassA = a;
+    *msPassB = b;
+    *steps = (int32_t) n;
+    d->profUsed = 0;
+    return VVB200_OK;
+}
+
 extern "C" int vvb200_middle_kick_reduce(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
     int rc = checkStepArgs(p, b, "vvb200_middle_kick_reduce", false, true);
     if (rc) return rc;
@@ -1458,8 +1517,10 @@ extern "C" int vvb200_middle_kick_reduce(vvb200_plan *p, const vvb200_buffers *b
     if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
     KParams k = makeParams(p, b, a);
     k.fuseNHC = 0;
+    profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, p->par.cos_acceleration != 0, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 1, st);
     return VVB200_OK;
 }
 
@@ -1479,8 +1540,11 @@ extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffer
     cudaStream_t st = (cudaStream_t) stream;
     if (hasNH(p) && (rc = launchNhc(p, st))) return rc;
     KParams k = makeParams(p, b, a);
+    // the pass-B interval of the split path starts here (the all-reduce and the NHC block are not in it)
+    profMark(p->dev, 2, st);
     CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, p->par.cos_acceleration != 0, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 3, st);
     return vvb200_update_image_positions(p, b, stream);
 }
 
@@ -1502,10 +1566,14 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
     if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
+    profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 1, st);
+    profMark(p->dev, 2, st);
     CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 3, st);
     return vvb200_update_image_positions(p, b, stream);
 }
 

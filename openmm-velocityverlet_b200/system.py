@@ -249,6 +249,8 @@ def make_ragged(seed=0, n_molecules=60, max_size=40, drude_fraction=0.3, massles
                 if masses[i] == 1.008 and not in_pair[i] and not in_pair[a] and rng.random() < 0.5:
                     cons.append((int(a), i))
     free = np.flatnonzero(~in_pair)
+    free = np.setdiff1d(free, starts[:-1])      # keep one massive site per molecule (an all-massless NH
+                                                # molecule is 0*inf = NaN in the reference's COM kernel)
     massless = rng.choice(free, size=int(massless_fraction * len(free)), replace=False) if len(free) else []
     masses[massless] = 0.0
     langevin = np.concatenate([np.arange(starts[m], starts[m + 1]) for m in sorted(ld_mols)]) if ld_mols else []

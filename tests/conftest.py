@@ -43,7 +43,26 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b) / scale))
 
 
-# tolerances of the parity plan: single frozen-force substep, relative error on x and v
-TOL = {"mixed": 1e-6, "double": 1e-12, "single": 1e-5}
+def rms_err(a, b):
+    """max |a-b| / max(|b|, rms(b)): the single-precision metric.  With 24-bit arithmetic the thermostat's
+    (v - V_mol) + V_mol round trip and the hard wall's x_drude - x_parent cancellation leave an ABSOLUTE error of
+    a few ulp of the vector's magnitude in every component, so small components carry no relative accuracy."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    scale = np.maximum(np.abs(b), np.sqrt(np.mean(b * b)) + 1e-300)
+    return float(np.max(np.abs(a - b) / scale))
+
+
+# THE BAR (BASELINE.json north_star): positions and velocities after frozen-force steps within 1e-6 relative in
+# mixed precision, with rel = rel_err above; 1e-8 in double (velocity arithmetic is fp64 in both).  Single precision: 1e-5 with rms_err (1e-4 once the
+# Drude hard wall has fired: its bond direction is a float difference of O(1) positions 0.02 nm apart).
+TOL = {"mixed": 1e-6, "double": 1e-8, "single": 1e-5}
+# What the tests actually assert for mixed/double: the library is built without FMA contraction, like the CPU
+# oracle, so the two agree far below the bar (observed <= 3e-13 without / 6e-11 with the hard wall, whose
+# r - maxDrudeDistance cancellation amplifies last-bit differences of exp/sqrt).
+TIGHT = {"mixed": 1e-11, "double": 1e-11, "single": 1e-5}
+TIGHT_HARDWALL = {"mixed": 1e-8, "double": 1e-8, "single": 1e-4}
 # scale factors / group energies
 TOL_KE = {"mixed": 1e-12, "double": 1e-12, "single": 1e-5}
