@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,11 +35,8 @@
 #define BOLTZ_D (1.380649e-23 * 6.02214076e23 / 1000.0)
 #define AVOGADRO_D 6.02214076e23
 
-#define THREADS 256
-#define VVB200_MAX_BLOCKS_PER_SM 8
-#define ITEMS (VVB200_TILE_CAP / THREADS)
-static_assert(VVB200_TILE_CAP % THREADS == 0, "tile must be a multiple of the block");
-static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
+#define THREADS 256                       // block size of the small element-wise kernels
+#define VVB200_MAX_BLOCKS_PER_SM 4
 
 // ------------------------------------------------------------------------------------------------
 // precision traits: OpenMM's CudaPrecision modes
@@ -116,7 +114,8 @@ struct NhcDevice {
 
 struct KParams {
     int N, paddedN, numTiles;
-    const int32_t *tileStart, *tileMolOffset, *tileMolList, *tileMolInfo;
+    const int4 *tileDesc;                      // 2 x int4 per tile, see vvb200_stream.cuh
+    const int32_t *tileMolList, *tileMolInfo;
     const uint32_t *slotMeta;
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
@@ -130,7 +129,8 @@ struct KParams {
     unsigned int *counter;
     double dt;
     double efscale, accel, invBoxZ, maxDrudeDistance, hardwallScale;
-    int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC;
+    int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC, cosine;
+    int stagesA, stagesB;
 };
 
 enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
@@ -210,638 +210,7 @@ __global__ void nhc_kernel(NhcDevice *s, double dt) {
         nhcFinish<COS>(s, dt, threadIdx.x);
 }
 
-// ------------------------------------------------------------------------------------------------
-// pass A
-// ------------------------------------------------------------------------------------------------
-template <int MODE, bool COS> struct SmemA {
-    typedef typename Prec<MODE>::mixed mixed;
-    mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], w[VVB200_TILE_CAP];
-    double cphase[COS ? VVB200_TILE_CAP : 1];   // cos(2*pi*z/Lz) is always evaluated in fp64
-    // per tile-local molecule: COM velocity and 1/M (and mass-weighted mean phase for COS)
-    mixed Vx[VVB200_TILE_CAP], Vy[VVB200_TILE_CAP], Vz[VVB200_TILE_CAP];
-    mixed cbar[COS ? VVB200_TILE_CAP : 1];
-    double red[THREADS / 32][VVB200_NRED];
-    unsigned int ticket;
-};
-
-template <int MODE, bool COS, int KICK>
-__global__ void __launch_bounds__(THREADS) kick_reduce_kernel(const KParams p) {
-    typedef Prec<MODE> P;
-    typedef typename P::real real;
-    typedef typename P::mixed mixed;
-    typedef typename P::real4 real4;
-    typedef typename P::mixed4 mixed4;
-    typedef typename P::real3 real3;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    SmemA<MODE, COS> &sm = *reinterpret_cast<SmemA<MODE, COS> *>(smemRaw);
-
-    const int tid = threadIdx.x;
-    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
-    const real4 *posq = reinterpret_cast<const real4 *>(p.posq);
-    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
-    mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
-    mixed *comCbar = reinterpret_cast<mixed *>(p.comCbar);
-
-    const mixed stepSize = (mixed) p.dt;
-    // middle.cu:11-12 / CudaVVKernels.cpp:306
-    const mixed fscale = KICK == KICK_VV ? (mixed) (0.5 * p.dt / (double) 0x100000000)
-                                         : stepSize / (mixed) 0x100000000;
-    const real efscale = (real) p.efscale;
-    const real accel = (real) p.accel;
-    const real invBoxZ = (real) p.invBoxZ;
-
-    // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
-    mixed acc[VVB200_NRED];
-#pragma unroll
-    for (int k = 0; k < VVB200_NRED; k++) acc[k] = 0;
-
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        const int t0 = p.tileStart[tile], t1 = p.tileStart[tile + 1];
-        const int m0 = p.tileMolOffset[tile], nMol = p.tileMolOffset[tile + 1] - m0;
-
-        mixed4 vel[ITEMS];
-        uint32_t meta[ITEMS];
-        // ---- phase 1: loads, extra forces, kick, stage --------------------------------------
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const int loc = it * THREADS + tid;
-            const int idx = t0 + loc;
-            const bool valid = idx < t1;
-            meta[it] = VVB200_META_MOL_NONE;
-            vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
-            double cph = 0;
-            if (valid) {
-                meta[it] = __ldg(p.slotMeta + idx);
-                mixed4 v = ld_stream(velm + idx);
-                if (COS)
-                    cph = cosPhase((double) posq[idx].z, (double) invBoxZ);
-                if (KICK != KICK_NONE && v.w != 0) {
-                    const long long fx = ld_force(p.force + idx);
-                    const long long fy = ld_force(p.force + idx + p.paddedN);
-                    const long long fz = ld_force(p.force + idx + 2 * (size_t) p.paddedN);
-                    // forceExtra as the reference builds it: reset, += Langevin, += field, += cosine
-                    real ex = 0, ey = 0, ez = 0;
-                    if (p.extraForces) {
-                        if (p.hasLD && (meta[it] & VVB200_META_LD)) {
-                            const real3 f = ldForce[p.ldSlot[idx]];
-                            ex = f.x; ey = f.y; ez = f.z;
-                        }
-                        if (p.hasField) {
-                            const int cnt = (meta[it] >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
-                            if (cnt) {
-                                const real q = posq[idx].w;
-                                for (int c = 0; c < cnt; c++)
-                                    ez += efscale * q;                         // electricField.cu:10
-                            }
-                        }
-                        if (COS)   // cosineAccelerate.cu:9 (float += double unless double mode)
-                            ex = (real) (ex + accel * cph * vv_recip(v.w));
-                    }
-                    if (KICK == KICK_MIDDLE) {   // middle.cu:17-19
-                        v.x += stepSize * v.w * ex + fscale * v.w * fx;
-                        v.y += stepSize * v.w * ey + fscale * v.w * fy;
-                        v.z += stepSize * v.w * ez + fscale * v.w * fz;
-                    } else {                      // velocityVerlet.cu:19-21 (0.5 is a double literal)
-                        v.x += 0.5 * stepSize * v.w * ex + fscale * v.w * fx;
-                        v.y += 0.5 * stepSize * v.w * ey + fscale * v.w * fy;
-                        v.z += 0.5 * stepSize * v.w * ez + fscale * v.w * fz;
-                    }
-                    st_stream(velm + idx, v);
-                }
-                vel[it] = v;
-                if (COS && v.w != 0)   // cosineAccelerate.cu:26
-                    acc[3] += vv_recip(v.w) * v.x * 2 * cph;
-            }
-            sm.vx[loc] = vel[it].x; sm.vy[loc] = vel[it].y; sm.vz[loc] = vel[it].z; sm.w[loc] = vel[it].w;
-            if (COS) sm.cphase[loc] = cph;
-        }
-        __syncthreads();
-
-        // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), one
-        //      thread per molecule, particles in ascending order like particlesSortedByMolId ----
-        if (p.useCOM) {
-            for (int j = tid; j < nMol; j += THREADS) {
-                const uint32_t info = (uint32_t) p.tileMolInfo[m0 + j];
-                const int mol = p.tileMolList[m0 + j];
-                mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
-                if (!MOLINFO_SCATTERED(info)) {
-                    const int first = MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
-                    for (int k = first; k < first + cnt; k++) {
-                        const mixed w = sm.w[k];
-                        if (w != 0) {
-                            const mixed mass = vv_recip(w);
-                            sx += sm.vx[k] * mass; sy += sm.vy[k] * mass; sz += sm.vz[k] * mass;
-                            if (COS) sc += sm.cphase[k] * mass;
-                            comMass += mass;
-                        }
-                    }
-                } else {
-                    const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
-                    for (int k = 0; k < cnt; k++) {
-                        const int loc = p.sortedByMol[start + k] - t0;
-                        if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
-                        const mixed w = sm.w[loc];
-                        if (w != 0) {
-                            const mixed mass = vv_recip(w);
-                            sx += sm.vx[loc] * mass; sy += sm.vy[loc] * mass; sz += sm.vz[loc] * mass;
-                            if (COS) sc += sm.cphase[loc] * mass;
-                            comMass += mass;
-                        }
-                    }
-                }
-                mixed4 V;
-                V.w = vv_recip(comMass);
-                V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
-                sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
-                st_stream(comV + mol, V);
-                mixed cb = 0;
-                if (COS) {
-                    cb = sc * V.w;
-                    sm.cbar[j] = cb;
-                    comCbar[mol] = cb;
-                }
-                // molecular temperature group (drudeNoseHoover.cu:91-97)
-                if (V.w != 0) {
-                    const mixed M = 1 / V.w;   // only used by the COS moments
-                    acc[1] += (V.x * V.x + V.y * V.y + V.z * V.z) / V.w;
-                    if (COS) {
-                        acc[5] += M * V.x * cb;
-                        acc[8] += M * cb * cb;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- phase 3: group kinetic energies of the COM-normalised velocities ------------------
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const uint32_t mw = meta[it];
-            if (!(mw & VVB200_META_NH)) continue;
-            const int loc = it * THREADS + tid;
-            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
-            const uint32_t lm = mw & VVB200_META_MOL_MASK;
-            mixed Vx = 0, Vy = 0, Vz = 0, cb = 0;
-            if (p.useCOM && lm != VVB200_META_MOL_NONE) {
-                Vx = sm.Vx[lm]; Vy = sm.Vy[lm]; Vz = sm.Vz[lm];
-                if (COS) cb = sm.cbar[lm];
-            }
-            const mixed4 v = vel[it];
-            if (role == VVB200_ROLE_NONE) {
-                if (v.w != 0) {   // drudeNoseHoover.cu:76-83
-                    const mixed ux = v.x - Vx, uy = v.y - Vy, uz = v.z - Vz;
-                    acc[0] += (ux * ux + uy * uy + uz * uz) / v.w;
-                    if (COS) {
-                        const mixed d = sm.cphase[loc] - cb;
-                        acc[4] += ux * d / v.w;
-                        acc[7] += d * d / v.w;
-                    }
-                }
-            } else if (role == VVB200_ROLE_DRUDE) {   // drudeNoseHoover.cu:99-114; this thread owns the pair
-                const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-                const mixed w1 = v.w, w2 = sm.w[ploc];
-                const mixed u1x = v.x - Vx, u1y = v.y - Vy, u1z = v.z - Vz;
-                const mixed u2x = sm.vx[ploc] - Vx, u2y = sm.vy[ploc] - Vy, u2z = sm.vz[ploc] - Vz;
-                const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
-                const mixed invTotalMass = vv_recip(mass1 + mass2);
-                const mixed invReducedMass = (mass1 + mass2) * w1 * w2;
-                const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
-                const mixed cmx = u1x * m1f + u2x * m2f, cmy = u1y * m1f + u2y * m2f, cmz = u1z * m1f + u2z * m2f;
-                const mixed rx = u1x - u2x, ry = u1y - u2y, rz = u1z - u2z;
-                acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * (mass1 + mass2);
-                acc[2] += (rx * rx + ry * ry + rz * rz) / invReducedMass;
-                if (COS) {
-                    const mixed d1 = sm.cphase[loc] - cb, d2 = sm.cphase[ploc] - cb;
-                    const mixed cmd = d1 * m1f + d2 * m2f, rd = d1 - d2;
-                    acc[4] += cmx * cmd * (mass1 + mass2);
-                    acc[7] += cmd * cmd * (mass1 + mass2);
-                    acc[6] += rx * rd / invReducedMass;
-                    acc[9] += rd * rd / invReducedMass;
-                }
-            }
-        }
-        __syncthreads();   // shared staging is reused by the next tile
-    }
-
-    // ---- block reduction (fixed order), then the last block finishes ----------------------------
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NR = COS ? VVB200_NRED : 3;
-#pragma unroll
-    for (int k = 0; k < NR; k++) {
-        double v = (double) acc[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0) sm.red[warp][k] = v;
-    }
-    __syncthreads();
-    if (tid < NR) {
-        double v = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; w++) v += sm.red[w][tid];
-        p.partials[(size_t) blockIdx.x * VVB200_NRED + tid] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0)
-        sm.ticket = atomicAdd(p.counter, 1u);
-    __syncthreads();
-    if (sm.ticket != gridDim.x - 1)
-        return;
-    // last block: sum the per-block partials block-major in a fixed order
-    __threadfence();
-    for (int k = 0; k < NR; k++) {
-        double v = 0;
-        for (int b = tid; b < (int) gridDim.x; b += THREADS)
-            v += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0) sm.red[warp][k] = v;
-    }
-    __syncthreads();
-    if (tid < VVB200_NRED) {
-        double v = 0;
-        if (tid < NR)
-            for (int w = 0; w < THREADS / 32; w++) v += sm.red[w][tid];
-        p.nhc->red[tid] = v;
-    }
-    if (tid == 0)
-        *p.counter = 0;
-    __syncthreads();
-    if (p.fuseNHC && tid < 3)
-        nhcFinish<COS>(p.nhc, p.dt, tid);
-}
-
-// ------------------------------------------------------------------------------------------------
-// pass B
-// ------------------------------------------------------------------------------------------------
-template <int MODE, bool COS, bool POS> struct SmemB {
-    typedef typename Prec<MODE>::mixed mixed;
-    mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], w[VVB200_TILE_CAP];
-    mixed px[POS ? VVB200_TILE_CAP : 1], py[POS ? VVB200_TILE_CAP : 1], pz[POS ? VVB200_TILE_CAP : 1];
-    double cphase[COS ? VVB200_TILE_CAP : 1];
-    mixed Vx[VVB200_TILE_CAP], Vy[VVB200_TILE_CAP], Vz[VVB200_TILE_CAP];
-    mixed cbar[COS ? VVB200_TILE_CAP : 1];
-};
-
-// thermostat scaling of one particle given its partner (drudeNoseHoover.cu:164-208).  v* are
-// COM-normalised (and bias-free) velocities; returns the new absolute velocity of `self`.
-template <class mixed>
-__device__ __forceinline__ void scalePair(const mixed v1[3], mixed w1, const mixed v2[3], mixed w2, const mixed V[3],
-                                          mixed sA, mixed sC, mixed sD, mixed out1[3], mixed out2[3]) {
-    const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
-    const mixed invTotalMass = vv_recip(mass1 + mass2);
-    const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        mixed cm = v1[d] * m1f + v2[d] * m2f;
-        mixed rel = v2[d] - v1[d];
-        cm = sA * cm;
-        rel = sD * rel;
-        out1[d] = cm - rel * m2f + sC * V[d];
-        out2[d] = cm + rel * m1f + sC * V[d];
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void splitPos(typename Prec<MODE>::mixed x, typename Prec<MODE>::real &hi,
-                                         typename Prec<MODE>::real &lo) {
-    typedef typename Prec<MODE>::real real;
-    hi = (real) x;
-    lo = (real) (x - (typename Prec<MODE>::mixed) hi);
-}
-
-template <int MODE, bool COS, int VARIANT>
-__global__ void __launch_bounds__(THREADS) scale_drift_kernel(const KParams p) {
-    typedef Prec<MODE> P;
-    typedef typename P::real real;
-    typedef typename P::mixed mixed;
-    typedef typename P::real4 real4;
-    typedef typename P::mixed4 mixed4;
-    typedef typename P::real3 real3;
-    constexpr bool POS = VARIANT != VAR_SCALE_ONLY;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    SmemB<MODE, COS, POS> &sm = *reinterpret_cast<SmemB<MODE, COS, POS> *>(smemRaw);
-
-    const int tid = threadIdx.x;
-    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
-    real4 *posq = reinterpret_cast<real4 *>(p.posq);
-    real4 *corr = reinterpret_cast<real4 *>(p.corr);
-    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
-    const mixed4 *comV = reinterpret_cast<const mixed4 *>(p.comV);
-    const mixed *comCbar = reinterpret_cast<const mixed *>(p.comCbar);
-
-    const mixed stepSize = (mixed) p.dt;
-    const mixed halfdt = 0.5f * stepSize;                       // middle.cu:33,51
-    const mixed invStepSize = (mixed) (1.0 / stepSize);         // velocityVerlet.cu:40
-    const mixed fscaleVV = (mixed) (0.5 * p.dt / (double) 0x100000000);
-    const mixed sA = (mixed) p.nhc->vscale[0], sC = (mixed) p.nhc->vscale[1], sD = (mixed) p.nhc->vscale[2];
-    const mixed Vb = COS ? (mixed) p.nhc->vBias : (mixed) 0;
-    const mixed maxD = (mixed) p.maxDrudeDistance;
-    const mixed hwScale = (mixed) p.hardwallScale;
-    const real efscale = (real) p.efscale;
-    const real accel = (real) p.accel;
-    const real invBoxZ = (real) p.invBoxZ;
-
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        const int t0 = p.tileStart[tile], t1 = p.tileStart[tile + 1];
-        const int m0 = p.tileMolOffset[tile], nMol = p.tileMolOffset[tile + 1] - m0;
-
-        mixed4 vel[ITEMS];
-        real4 pq[ITEMS];
-        mixed pos[ITEMS][3];
-        uint32_t meta[ITEMS];
-        double cph[ITEMS];
-        // ---- phase 1: load + stage ---------------------------------------------------------------
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const int loc = it * THREADS + tid;
-            const int idx = t0 + loc;
-            meta[it] = VVB200_META_MOL_NONE;
-            vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
-            pos[it][0] = pos[it][1] = pos[it][2] = 0;
-            cph[it] = 0;
-            if (idx < t1) {
-                meta[it] = __ldg(p.slotMeta + idx);
-                vel[it] = ld_stream(velm + idx);
-                if (POS || COS) {
-                    pq[it] = ld_stream(posq + idx);
-                    if (P::kMixed) {
-                        const real4 c = ld_stream(corr + idx);
-                        pos[it][0] = pq[it].x + (mixed) c.x;       // middle.cu:82-84
-                        pos[it][1] = pq[it].y + (mixed) c.y;
-                        pos[it][2] = pq[it].z + (mixed) c.z;
-                    } else {
-                        pos[it][0] = pq[it].x; pos[it][1] = pq[it].y; pos[it][2] = pq[it].z;
-                    }
-                    if (COS) cph[it] = cosPhase((double) pq[it].z, (double) invBoxZ);
-                }
-            }
-            sm.vx[loc] = vel[it].x; sm.vy[loc] = vel[it].y; sm.vz[loc] = vel[it].z; sm.w[loc] = vel[it].w;
-            if (POS) { sm.px[loc] = pos[it][0]; sm.py[loc] = pos[it][1]; sm.pz[loc] = pos[it][2]; }
-            if (COS) sm.cphase[loc] = cph[it];
-        }
-        if (p.useCOM) {
-            for (int j = tid; j < nMol; j += THREADS) {
-                const int mol = p.tileMolList[m0 + j];
-                const mixed4 V = comV[mol];
-                sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
-                if (COS) sm.cbar[j] = comCbar[mol];
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: per particle ------------------------------------------------------------------
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const int loc = it * THREADS + tid;
-            const int idx = t0 + loc;
-            if (idx >= t1) continue;
-            const uint32_t mw = meta[it];
-            const bool isNH = mw & VVB200_META_NH;
-            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
-            const uint32_t lm = mw & VVB200_META_MOL_MASK;
-            const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-            const bool hasMol = p.useCOM && lm != VVB200_META_MOL_NONE;
-            mixed V[3] = {0, 0, 0};
-            mixed cb = 0;
-            if (hasMol) {
-                V[0] = sm.Vx[lm]; V[1] = sm.Vy[lm]; V[2] = sm.Vz[lm];
-                if (COS) cb = sm.cbar[lm];
-            }
-            // this particle ("s") and, for pair roles, its partner ("q")
-            mixed vs[3] = {vel[it].x, vel[it].y, vel[it].z};
-            const mixed ws = vel[it].w;
-            mixed vq[3] = {0, 0, 0}, wq = 0;
-            double cq = 0;
-            if (role != VVB200_ROLE_NONE) {
-                vq[0] = sm.vx[ploc]; vq[1] = sm.vy[ploc]; vq[2] = sm.vz[ploc]; wq = sm.w[ploc];
-                if (COS) cq = sm.cphase[ploc];
-            }
-            // velocities entering the drift as "pre-thermostat" values (middle.cu:33-41)
-            const mixed vs0[3] = {vs[0], vs[1], vs[2]};
-            const mixed vq0[3] = {vq[0], vq[1], vq[2]};
-            bool writeVel = false;
-
-            if (isNH) {
-                // removePeriodicVelocityBias (all atoms; only matters for thermostatted ones here since
-                // remove and restore cancel exactly elsewhere -- they do not: see below)
-                if (COS) { vs[0] -= Vb * cph[it]; vq[0] -= Vb * cq; }
-                // bias-removed molecular velocity: V' = V - Vb*cbar e_x
-                mixed Vn[3] = {V[0], V[1], V[2]};
-                if (COS && hasMol) Vn[0] = V[0] - Vb * cb;
-                if (hasMol) {   // normalizeVelocities, drudeNoseHoover.cu:42-48
-#pragma unroll
-                    for (int d = 0; d < 3; d++) { vs[d] -= Vn[d]; vq[d] -= Vn[d]; }
-                }
-                if (role == VVB200_ROLE_NONE) {
-                    if (ws != 0) {
-#pragma unroll
-                        for (int d = 0; d < 3; d++) vs[d] = sA * vs[d] + sC * Vn[d];   // drudeNoseHoover.cu:172-176
-                    }
-                    writeVel = COS || hasMol || ws != 0;
-                } else {
-                    mixed o1[3], o2[3];
-                    if (role == VVB200_ROLE_DRUDE) {
-                        scalePair<mixed>(vs, ws, vq, wq, Vn, sA, sC, sD, o1, o2);
-#pragma unroll
-                        for (int d = 0; d < 3; d++) { vs[d] = o1[d]; vq[d] = o2[d]; }
-                    } else {
-                        scalePair<mixed>(vq, wq, vs, ws, Vn, sA, sC, sD, o1, o2);
-#pragma unroll
-                        for (int d = 0; d < 3; d++) { vq[d] = o1[d]; vs[d] = o2[d]; }
-                    }
-                    writeVel = true;
-                }
-                if (COS) { vs[0] += Vb * cph[it]; vq[0] += Vb * cq; }   // restorePeriodicVelocityBias
-            } else if (COS) {
-                // non-thermostatted atoms still see remove then restore (cosineAccelerate.cu:63-84)
-                vs[0] -= Vb * cph[it]; vs[0] += Vb * cph[it];
-                vq[0] -= Vb * cq; vq[0] += Vb * cq;
-                writeVel = true;
-            }
-
-            if (VARIANT == VAR_SCALE_ONLY) {
-                if (writeVel) {
-                    mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
-                    st_stream(velm + idx, o);
-                }
-                continue;
-            }
-
-            mixed xs[3] = {pos[it][0], pos[it][1], pos[it][2]};
-            mixed xq[3] = {0, 0, 0};
-            if (role != VVB200_ROLE_NONE) { xq[0] = sm.px[ploc]; xq[1] = sm.py[ploc]; xq[2] = sm.pz[ploc]; }
-            bool writePos = false;
-
-            if (VARIANT == VAR_VV_FIRST) {
-                // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
-                // particle and (redundantly) its partner
-                for (int who = 0; who < 2; who++) {
-                    if (who == 1 && role == VVB200_ROLE_NONE) break;
-                    const int j = who == 0 ? idx : t0 + ploc;
-                    mixed *v = who == 0 ? vs : vq;
-                    const mixed w = who == 0 ? ws : wq;
-                    if (w == 0) continue;
-                    const uint32_t mj = who == 0 ? mw : __ldg(p.slotMeta + j);
-                    real ex = 0, ey = 0, ez = 0;
-                    if (p.extraForces) {
-                        if (p.hasLD && (mj & VVB200_META_LD)) {
-                            const real3 f = ldForce[p.ldSlot[j]];
-                            ex = f.x; ey = f.y; ez = f.z;
-                        }
-                        if (p.hasField) {
-                            const int cnt = (mj >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
-                            const real q = who == 0 ? pq[it].w : posq[j].w;
-                            for (int c = 0; c < cnt; c++) ez += efscale * q;
-                        }
-                        if (COS) {
-                            const double c = who == 0 ? cph[it] : cq;
-                            ex = (real) (ex + accel * c * vv_recip(w));
-                        }
-                    }
-                    const long long fx = ld_force(p.force + j);
-                    const long long fy = ld_force(p.force + j + p.paddedN);
-                    const long long fz = ld_force(p.force + j + 2 * (size_t) p.paddedN);
-                    v[0] += 0.5 * stepSize * w * ex + fscaleVV * w * fx;
-                    v[1] += 0.5 * stepSize * w * ey + fscaleVV * w * fy;
-                    v[2] += 0.5 * stepSize * w * ez + fscaleVV * w * fz;
-                }
-                // posDelta = dt*v ; x += posDelta ; v = posDelta/dt  (velocityVerlet.cu:25,52-58)
-                if (ws != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        const mixed delta = stepSize * vs[d];
-                        xs[d] += delta;
-                        vs[d] = (mixed) (invStepSize * delta);
-                    }
-                    writePos = writeVel = true;
-                }
-                if (role != VVB200_ROLE_NONE && wq != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        const mixed delta = stepSize * vq[d];
-                        xq[d] += delta;
-                        vq[d] = (mixed) (invStepSize * delta);
-                    }
-                }
-            } else {
-                // middle scheme without constraints: posDelta = oldDelta = halfdt*v0 + halfdt*v', so
-                // integrateMiddlePos3 leaves v' unchanged and moves x by posDelta (middle.cu:33-98)
-                if (ws != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        mixed delta = halfdt * vs0[d];
-                        delta += halfdt * vs[d];
-                        xs[d] += delta;
-                    }
-                    writePos = writeVel = true;
-                }
-                if (role != VVB200_ROLE_NONE && wq != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        mixed delta = halfdt * vq0[d];
-                        delta += halfdt * vq[d];
-                        xq[d] += delta;
-                    }
-                }
-            }
-
-            // ---- Drude hard wall (middle.cu:114-220), evaluated by both members of the pair ----------
-            if (p.hardwall && role != VVB200_ROLE_NONE) {
-                // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
-                if (P::kMixed) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        real hi, lo;
-                        if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
-                        if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
-                    }
-                } else if (MODE == VVB200_SINGLE) {
-                    // positions are already `real`
-                }
-                const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
-                mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
-                mixed *vel1 = selfIsDrude ? vs : vq, *vel2 = selfIsDrude ? vq : vs;
-                const mixed w1 = selfIsDrude ? ws : wq, w2 = selfIsDrude ? wq : ws;
-                const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
-                const mixed r = vv_sqrt<MODE, mixed>(dx * dx + dy * dy + dz * dz);
-                const mixed rInv = vv_recip(r);
-                if (rInv * maxD < 1) {
-                    const mixed bond[3] = {dx * rInv, dy * rInv, dz * rInv};
-                    const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
-                    const mixed deltaR = r - maxD;
-                    mixed deltaT = stepSize;
-                    mixed dotvr1 = vel1[0] * bond[0] + vel1[1] * bond[1] + vel1[2] * bond[2];
-                    mixed vp1[3];
-#pragma unroll
-                    for (int d = 0; d < 3; d++) vp1[d] = vel1[d] - bond[d] * dotvr1;
-                    if (w2 == 0) {
-                        if (dotvr1 != 0) deltaT = deltaR / fabs(dotvr1);
-                        if (deltaT > stepSize) deltaT = stepSize;
-                        dotvr1 = -dotvr1 * hwScale / (fabs(dotvr1) * vv_sqrt<MODE, mixed>(mass1));
-                        const mixed dr = -deltaR + deltaT * dotvr1;
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            pos1[d] += bond[d] * dr;
-                            vel1[d] = vp1[d] + bond[d] * dotvr1;
-                        }
-                    } else {
-                        const mixed invTotalMass = vv_recip(mass1 + mass2);
-                        mixed dotvr2 = vel2[0] * bond[0] + vel2[1] * bond[1] + vel2[2] * bond[2];
-                        mixed vp2[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) vp2[d] = vel2[d] - bond[d] * dotvr2;
-                        const mixed vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
-                        dotvr1 -= vbCMass;
-                        dotvr2 -= vbCMass;
-                        if (dotvr1 != dotvr2) deltaT = deltaR / fabs(dotvr1 - dotvr2);
-                        if (deltaT > stepSize) deltaT = stepSize;
-                        const mixed vBond = hwScale / vv_sqrt<MODE, mixed>(mass1);
-                        dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabs(dotvr1);
-                        dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabs(dotvr2);
-                        const mixed dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
-                        const mixed dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
-                        dotvr1 += vbCMass;
-                        dotvr2 += vbCMass;
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            pos1[d] += bond[d] * dr1;
-                            pos2[d] += bond[d] * dr2;
-                            vel1[d] = vp1[d] + bond[d] * dotvr1;
-                            vel2[d] = vp2[d] + bond[d] * dotvr2;
-                        }
-                    }
-                    // the reference writes the touched members unconditionally (middle.cu:166-172, 204-219)
-                    if (selfIsDrude || w2 != 0) writePos = writeVel = true;
-                }
-            }
-
-            if (writeVel) {
-                mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
-                st_stream(velm + idx, o);
-            }
-            if (writePos) {
-                real4 o;
-                if (P::kMixed) {
-                    real4 oc;
-                    splitPos<MODE>(xs[0], o.x, oc.x);
-                    splitPos<MODE>(xs[1], o.y, oc.y);
-                    splitPos<MODE>(xs[2], o.z, oc.z);
-                    o.w = pq[it].w;
-                    oc.w = 0;
-                    st_stream(posq + idx, o);
-                    st_stream(corr + idx, oc);
-                } else {
-                    o.x = (real) xs[0]; o.y = (real) xs[1]; o.z = (real) xs[2]; o.w = pq[it].w;
-                    st_stream(posq + idx, o);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
+#include "vvb200_stream.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // small gather kernels
@@ -1119,7 +488,9 @@ struct vvb200_device_state {
     int device = 0;
     int numSM = 148;
     int numTiles = 0;
-    int32_t *tileStart = nullptr, *tileMolOffset = nullptr, *tileMolList = nullptr, *tileMolInfo = nullptr;
+    int4 *tileDesc = nullptr;
+    int32_t *tileMolList = nullptr, *tileMolInfo = nullptr;
+    int stagesA = 0, stagesB = 0, blocksPerSM = 0;   // 0: chosen per kernel from the shared-memory budget
     uint32_t *slotMeta = nullptr;
     int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
     int2 *pairsLD = nullptr, *imagePairs = nullptr, *drudePairs = nullptr;
@@ -1243,12 +614,24 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
             }
         }
     }
+    // tile descriptors: (t0, t1, m0, nMol), (molFirst or -1, 0, 0, 0)
+    std::vector<int32_t> desc((size_t) d->numTiles * 8, 0);
+    for (int t = 0; t < d->numTiles; t++) {
+        const int m0 = p->tileMolOffset[t], nMol = p->tileMolOffset[t + 1] - m0;
+        int molFirst = nMol > 0 ? p->tileMolList[m0] : 0;
+        for (int j = 0; j < nMol; j++)
+            if (p->tileMolList[m0 + j] != molFirst + j) molFirst = -1;
+        int32_t *e = desc.data() + (size_t) t * 8;
+        e[0] = p->tileStart[t]; e[1] = p->tileStart[t + 1]; e[2] = m0; e[3] = nMol; e[4] = molFirst;
+    }
+    molInfo.resize(molInfo.size() + 8, 0);                       // bulk copies read rounded-up ranges
+    std::vector<uint32_t> metaPadded(p->slotMeta);
+    metaPadded.resize((size_t) p->paddedN + 8, VVB200_META_MOL_NONE);
     int rc;
-    if ((rc = uploadVec(d, &d->tileStart, p->tileStart.data(), p->tileStart.size(), st))) return rc;
-    if ((rc = uploadVec(d, &d->tileMolOffset, p->tileMolOffset.data(), p->tileMolOffset.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->tileDesc, desc.data(), (size_t) d->numTiles * 2, st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolList, p->tileMolList.data(), p->tileMolList.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolInfo, molInfo.data(), molInfo.size(), st))) return rc;
-    if ((rc = uploadVec(d, &d->slotMeta, p->slotMeta.data(), p->slotMeta.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->slotMeta, metaPadded.data(), metaPadded.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->sortedByMol, p->sortedByMol.data(), p->sortedByMol.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->particlesInMolecules, p->particlesInMolecules.data(), p->particlesInMolecules.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->ldSlot, p->ldSlot.data(), p->ldSlot.size(), st))) return rc;
@@ -1261,7 +644,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     unsigned char *raw = nullptr;
     if ((rc = uploadVec(d, &raw, nullptr, (size_t) p->M * 4 * ms, st))) return rc;   // zero-initialised, :606-617
     d->comV = raw;
-    if ((rc = uploadVec(d, &raw, nullptr, (size_t) p->M * ms, st))) return rc;
+    if ((rc = uploadVec(d, &raw, nullptr, ((size_t) p->M + 8) * ms, st))) return rc;
     d->comCbar = raw;
     const size_t nLDslots = p->normalLD.size() + p->pairsLD.size();
     if ((rc = uploadVec(d, &raw, nullptr, std::max<size_t>(nLDslots, 1) * 3 * rs, st))) return rc;
@@ -1331,7 +714,7 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     KParams k;
     memset(&k, 0, sizeof k);
     k.N = p->N; k.paddedN = p->paddedN; k.numTiles = d->numTiles;
-    k.tileStart = d->tileStart; k.tileMolOffset = d->tileMolOffset; k.tileMolList = d->tileMolList;
+    k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
     k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
     k.posq = b->posq; k.corr = b->posq_correction; k.velm = b->velm; k.force = b->force;
@@ -1349,60 +732,87 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.hardwall = p->par.max_drude_distance > 0 && !p->drudePairs.empty();
     k.extraForces = 1;
     k.fuseNHC = 1;
+    k.cosine = p->par.cos_acceleration != 0;
     return k;
 }
 
-// Persistent launch geometry: one wave of co-resident blocks (148 SMs x blocks/SM from the occupancy
-// calculator), each striding over the molecule-aligned tiles.
-template <int MODE, bool COS, int KICK>
-static cudaError_t launchA(const KParams &k, int numSM, cudaStream_t st) {
-    const size_t smem = sizeof(SmemA<MODE, COS>);
-    static int perSM = 0;
-    if (!perSM) {
-        cudaFuncSetAttribute(kick_reduce_kernel<MODE, COS, KICK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kick_reduce_kernel<MODE, COS, KICK>, THREADS, smem);
-        perSM = std::max(1, std::min(perSM, VVB200_MAX_BLOCKS_PER_SM));
+// Persistent launch geometry: blocksPerSM co-resident blocks per SM (148 SMs), each with a ring of `stages`
+// shared-memory stages, striding over the molecule-aligned tiles.  Defaults: two blocks per SM, as many stages
+// as fit the 227 KB of shared memory (at least 2); VVB200_STAGES_A/B and VVB200_BLOCKS_PER_SM override (tuning).
+static int envInt(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+struct LaunchCfg { int stages, perSM; size_t smem; };
+
+template <class F>
+static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stagesEnv, int numSM) {
+    int dev = 0, maxOptin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    LaunchCfg c;
+    c.perSM = std::max(1, std::min(envInt("VVB200_BLOCKS_PER_SM", 2), VVB200_MAX_BLOCKS_PER_SM));
+    const size_t perSMBudget = 227 * 1024;
+    int stages = envInt(stagesEnv, 0);
+    if (stages <= 0) {
+        stages = 2;
+        while (stages < 8 && (smemBytes(stages + 1) + 1024) * c.perSM <= perSMBudget) stages++;
     }
-    const int grid = std::max(1, std::min(k.numTiles, numSM * perSM));
-    kick_reduce_kernel<MODE, COS, KICK><<<grid, THREADS, smem, st>>>(k);
+    while (stages > 1 && smemBytes(stages) > (size_t) maxOptin) stages--;
+    c.stages = stages;
+    c.smem = smemBytes(stages);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BTHREADS, c.smem);
+    c.perSM = std::max(1, std::min(c.perSM, occ));
+    (void) numSM;
+    return c;
+}
+
+template <int MODE, int KICK, bool EXTRA>
+static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
+    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", numSM);
+    k.stagesA = cfg.stages;
+    const int grid = std::max(1, std::min(k.numTiles, numSM * cfg.perSM));
+    kick_reduce_kernel<MODE, KICK, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
     return cudaGetLastError();
 }
 
-template <int MODE, bool COS, int VARIANT>
-static cudaError_t launchB(const KParams &k, int numSM, cudaStream_t st) {
-    const size_t smem = sizeof(SmemB<MODE, COS, VARIANT != VAR_SCALE_ONLY>);
-    static int perSM = 0;
-    if (!perSM) {
-        cudaFuncSetAttribute(scale_drift_kernel<MODE, COS, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, scale_drift_kernel<MODE, COS, VARIANT>, THREADS, smem);
-        perSM = std::max(1, std::min(perSM, VVB200_MAX_BLOCKS_PER_SM));
-    }
-    const int grid = std::max(1, std::min(k.numTiles, numSM * perSM));
-    scale_drift_kernel<MODE, COS, VARIANT><<<grid, THREADS, smem, st>>>(k);
+template <int MODE, int VARIANT, bool EXTRA>
+static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
+    static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", numSM);
+    k.stagesB = cfg.stages;
+    const int grid = std::max(1, std::min(k.numTiles, numSM * cfg.perSM));
+    scale_drift_kernel<MODE, VARIANT, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
     return cudaGetLastError();
 }
+
+// EXTRA kernels stage posq as well: needed by the external field (charge), the cosine acceleration (z) and, for
+// uniformity, Langevin systems (which are never large)
+static bool needsExtra(const KParams &k) { return k.cosine || k.hasField || k.hasLD; }
 
 template <int KICK>
-static cudaError_t dispatchA(int precision, bool cosine, const KParams &k, int numSM, cudaStream_t st) {
-    switch (precision * 2 + (cosine ? 1 : 0)) {
-    case 0: return launchA<VVB200_SINGLE, false, KICK>(k, numSM, st);
-    case 1: return launchA<VVB200_SINGLE, true, KICK>(k, numSM, st);
-    case 2: return launchA<VVB200_MIXED, false, KICK>(k, numSM, st);
-    case 3: return launchA<VVB200_MIXED, true, KICK>(k, numSM, st);
-    case 4: return launchA<VVB200_DOUBLE, false, KICK>(k, numSM, st);
-    default: return launchA<VVB200_DOUBLE, true, KICK>(k, numSM, st);
+static cudaError_t dispatchA(int precision, bool, const KParams &k, int numSM, cudaStream_t st) {
+    switch (precision * 2 + (needsExtra(k) ? 1 : 0)) {
+    case 0: return launchA<VVB200_SINGLE, KICK, false>(k, numSM, st);
+    case 1: return launchA<VVB200_SINGLE, KICK, true>(k, numSM, st);
+    case 2: return launchA<VVB200_MIXED, KICK, false>(k, numSM, st);
+    case 3: return launchA<VVB200_MIXED, KICK, true>(k, numSM, st);
+    case 4: return launchA<VVB200_DOUBLE, KICK, false>(k, numSM, st);
+    default: return launchA<VVB200_DOUBLE, KICK, true>(k, numSM, st);
     }
 }
 
 template <int VARIANT>
-static cudaError_t dispatchB(int precision, bool cosine, const KParams &k, int numSM, cudaStream_t st) {
-    switch (precision * 2 + (cosine ? 1 : 0)) {
-    case 0: return launchB<VVB200_SINGLE, false, VARIANT>(k, numSM, st);
-    case 1: return launchB<VVB200_SINGLE, true, VARIANT>(k, numSM, st);
-    case 2: return launchB<VVB200_MIXED, false, VARIANT>(k, numSM, st);
-    case 3: return launchB<VVB200_MIXED, true, VARIANT>(k, numSM, st);
-    case 4: return launchB<VVB200_DOUBLE, false, VARIANT>(k, numSM, st);
-    default: return launchB<VVB200_DOUBLE, true, VARIANT>(k, numSM, st);
+static cudaError_t dispatchB(int precision, bool, const KParams &k, int numSM, cudaStream_t st) {
+    switch (precision * 2 + (needsExtra(k) ? 1 : 0)) {
+    case 0: return launchB<VVB200_SINGLE, VARIANT, false>(k, numSM, st);
+    case 1: return launchB<VVB200_SINGLE, VARIANT, true>(k, numSM, st);
+    case 2: return launchB<VVB200_MIXED, VARIANT, false>(k, numSM, st);
+    case 3: return launchB<VVB200_MIXED, VARIANT, true>(k, numSM, st);
+    case 4: return launchB<VVB200_DOUBLE, VARIANT, false>(k, numSM, st);
+    default: return launchB<VVB200_DOUBLE, VARIANT, true>(k, numSM, st);
     }
 }
 

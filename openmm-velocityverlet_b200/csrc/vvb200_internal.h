@@ -34,6 +34,8 @@
 
 // particles per tile of the fused kernels (threads x items); must be <= 1024 (11-bit local ids)
 #define VVB200_TILE_CAP 512
+// thermostat molecules per tile (bounds the per-stage molecule tables of the fused kernels)
+#define VVB200_TILE_MAX_MOLS 128
 
 // reduction vector layout (fp64), per block partial and final:
 //  [0..2]  A_g : sum m u^2 per temperature group (u = velocity relative to molecule COM, bias-free)

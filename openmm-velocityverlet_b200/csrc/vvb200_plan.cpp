@@ -123,7 +123,7 @@ extern "C" int vvb200_plan_create(const vvb200_system *sys, const vvb200_params 
     }
     *out = nullptr;
     const int N = sys->num_particles, M = sys->num_molecules;
-    if (N <= 0 || M <= 0 || sys->padded_num_atoms < N || !sys->masses || !sys->particle_mol_id ||
+    if (N <= 0 || M <= 0 || sys->padded_num_atoms < N || sys->padded_num_atoms % 4 != 0 || !sys->masses || !sys->particle_mol_id ||
         precision < VVB200_SINGLE || precision > VVB200_DOUBLE || par->num_nh_chains < 1 ||
         par->num_nh_chains > VVB200_MAX_CHAINS || par->loops_per_step < 1 ||
         (sys->num_drude > 0 && !sys->drude_pairs) || (sys->num_constraints > 0 && !sys->constraints) ||
@@ -369,12 +369,22 @@ static bool buildTiles(vvb200_plan *p) {
     }
     for (int i = 1; i <= N; i++)
         cover[i] += cover[i - 1];
+    // molBefore[i] = thermostat molecules whose first COM member lies below slot i (a tile owns the
+    // molecules that start inside it, because no cut separates a molecule's members)
+    std::vector<int32_t> molBefore(N + 1, 0);
+    for (int m = 0; m < M; m++)
+        if (hi[m] >= 0)
+            molBefore[lo[m] + 1]++;
+    for (int i = 1; i <= N; i++)
+        molBefore[i] += molBefore[i - 1];
 
     p->tileStart.clear();
     p->tileStart.push_back(0);
     int32_t s = 0;
     while (s < N) {
         int32_t e = std::min(N, s + VVB200_TILE_CAP);
+        while (e > s + 1 && molBefore[e] - molBefore[s] > VVB200_TILE_MAX_MOLS)
+            e--;
         while (e > s && e < N && cover[e] != 0)
             e--;
         if (e == s) {

@@ -1,0 +1,837 @@
+// vvb200_stream.cuh -- the two streaming kernels of the fused integrator step (included by vvb200_device.cu).
+//
+// Both are persistent, warp-specialised kernels built around a TMA (cp.async.bulk) -> shared memory ring:
+//
+//   warp 8 (producer)   for every molecule-aligned tile of this block: waits for a free stage, arms the stage's
+//                       "full" mbarrier with the byte count and issues one bulk copy per input array
+//                       (velm, force x/y/z, posq, posqCorrection, the packed slot words, per-molecule tables);
+//   warps 0-7 (consumers, 256 threads, 2 particles each) wait on "full", do the arithmetic from shared memory,
+//                       write results straight from registers with 128/256-bit coalesced stores, and release the
+//                       stage through the "empty" mbarrier.
+//
+// The ring keeps `stages` x ~30-40 KB of loads in flight per block regardless of what the consumers are doing
+// (molecule COM phase, block barriers), which is what an HBM-bound kernel with ~100 B/particle and non-trivial
+// per-tile synchronisation needs to approach the copy roofline (Little: ~35 KB in flight per SM).
+//
+// A tile [t0,t1) starts at an arbitrary particle index; bulk copies need 16-byte alignment, so every array is
+// copied for the slot range [t0 & ~3, roundup4(t1)) and consumers index with the offset t0 - (t0 & ~3).
+#pragma once
+
+#define CTHREADS 256                          // consumer threads
+#define BTHREADS (CTHREADS + 32)              // + one producer warp
+#define ITEMS (VVB200_TILE_CAP / CTHREADS)
+#define PADT (VVB200_TILE_CAP + 8)            // stage slots: tile + alignment slack
+#define MAXMOL VVB200_TILE_MAX_MOLS
+static_assert(VVB200_TILE_CAP % CTHREADS == 0, "tile must be a multiple of the consumer count");
+static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
+
+// ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbarArriveExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulkLoad(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
+                 "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void consumerBarrier() { asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory"); }
+
+// tile descriptor (two int4 per tile, built by vvb200_plan_upload)
+//   d0 = (t0, t1, m0, nMol)   d1 = (molFirst or -1, 0, 0, 0)
+// molFirst >= 0: the tile's thermostat molecules are the consecutive ids molFirst .. molFirst+nMol-1
+
+template <int MODE, bool EXTRA> struct StageA {
+    typename Prec<MODE>::mixed4 velm[PADT];      // consumers overwrite it with (v', mass)
+    long long f[3][PADT];
+    uint32_t meta[PADT];
+    int32_t molInfo[MAXMOL + 8];
+    int32_t desc[8];
+    typename Prec<MODE>::real4 posq[EXTRA ? PADT : 1];
+    double cph[EXTRA ? PADT : 2];
+};
+
+template <int MODE, bool EXTRA> struct ScratchA {
+    typedef typename Prec<MODE>::mixed mixed;
+    mixed Vx[MAXMOL], Vy[MAXMOL], Vz[MAXMOL];
+    mixed cbar[EXTRA ? MAXMOL : 1];
+    double red[CTHREADS / 32][VVB200_NRED];
+    unsigned int ticket;
+};
+
+__host__ __device__ constexpr size_t roundUp128(size_t x) { return (x + 127) / 128 * 128; }
+
+template <int MODE, bool EXTRA> constexpr size_t smemBytesA(int stages) {
+    return roundUp128(sizeof(StageA<MODE, EXTRA>)) * stages + roundUp128(sizeof(ScratchA<MODE, EXTRA>)) + 16 * stages + 128;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass A: extra forces + kick + molecular COM + group kinetic energies (+ bias moments) + NH chains
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int KICK, bool EXTRA>
+__global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    typedef StageA<MODE, EXTRA> Stage;
+    typedef ScratchA<MODE, EXTRA> Scratch;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int stages = p.stagesA;
+    constexpr size_t stageBytes = roundUp128(sizeof(Stage));
+    Scratch &sm = *reinterpret_cast<Scratch *>(smemRaw + stageBytes * stages);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smemRaw + stageBytes * stages + roundUp128(sizeof(Scratch)));
+    uint64_t *empty = full + stages;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbarInit(full + s, 1);
+            mbarInit(empty + s, CTHREADS);
+        }
+        fenceBarrierInit();
+    }
+    __syncthreads();
+
+    const bool cosine = EXTRA && p.cosine;
+    const bool useCOM = p.useCOM;
+
+    if (tid >= CTHREADS) {
+        // ===== producer warp =====
+        if (tid != CTHREADS)
+            return;
+        int s = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+            const int4 d0 = __ldg(p.tileDesc + 2 * tile), d1 = __ldg(p.tileDesc + 2 * tile + 1);
+            mbarWait(empty + s, phase ^ 1);
+            Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+            const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
+            const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
+            st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
+            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u;
+            if (KICK != KICK_NONE) bytes += 3u * cnt * 8u;
+            if (EXTRA) bytes += cnt * (uint32_t) sizeof(real4);
+            mbarArriveExpectTx(full + s, bytes);
+            bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
+            if (KICK != KICK_NONE) {
+                bulkLoad(st.f[0], p.force + a0, cnt * 8u, full + s);
+                bulkLoad(st.f[1], p.force + a0 + p.paddedN, cnt * 8u, full + s);
+                bulkLoad(st.f[2], p.force + a0 + 2 * (size_t) p.paddedN, cnt * 8u, full + s);
+            }
+            bulkLoad(st.meta, p.slotMeta + a0, cnt * 4u, full + s);
+            if (mcnt) bulkLoad(st.molInfo, p.tileMolInfo + ma0, mcnt * 4u, full + s);
+            if (EXTRA) bulkLoad(st.posq, reinterpret_cast<const real4 *>(p.posq) + a0, cnt * (uint32_t) sizeof(real4), full + s);
+            if (++s == stages) { s = 0; phase ^= 1; }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
+    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
+    mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
+    mixed *comCbar = reinterpret_cast<mixed *>(p.comCbar);
+
+    const mixed stepSize = (mixed) p.dt;
+    // middle.cu:11-12 / CudaVVKernels.cpp:306
+    const mixed fscale = KICK == KICK_VV ? (mixed) (0.5 * p.dt / (double) 0x100000000)
+                                         : stepSize / (mixed) 0x100000000;
+    const real efscale = (real) p.efscale;
+    const real accel = (real) p.accel;
+    const real invBoxZ = (real) p.invBoxZ;
+
+    constexpr int NR = EXTRA ? VVB200_NRED : 3;
+    // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
+    mixed acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++) acc[k] = 0;
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        mbarWait(full + s, phase);
+        Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+        const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = st.desc[3], molFirst = st.desc[4];
+        const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
+
+        mixed4 vel[ITEMS];
+        uint32_t meta[ITEMS];
+        // ---- phase 1: extra forces, kick, store; publish (v', mass) to the tile ---------------------
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * CTHREADS + tid;
+            const int idx = t0 + loc, sl = sl0 + loc;
+            meta[it] = VVB200_META_MOL_NONE;
+            vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
+            if (idx < t1) {
+                meta[it] = st.meta[sl];
+                mixed4 v = st.velm[sl];
+                double cph = 0;
+                real q = 0;
+                if (EXTRA) {
+                    const real4 pq = st.posq[sl];
+                    q = pq.w;
+                    if (cosine) cph = cosPhase((double) pq.z, (double) invBoxZ);
+                }
+                if (KICK != KICK_NONE && v.w != 0) {
+                    const long long fx = st.f[0][sl], fy = st.f[1][sl], fz = st.f[2][sl];
+                    if (EXTRA) {
+                        // forceExtra as the reference builds it: reset, += Langevin, += field, += cosine
+                        real ex = 0, ey = 0, ez = 0;
+                        if (p.extraForces) {
+                            if (p.hasLD && (meta[it] & VVB200_META_LD)) {
+                                const real3 f = ldForce[p.ldSlot[idx]];
+                                ex = f.x; ey = f.y; ez = f.z;
+                            }
+                            if (p.hasField) {
+                                const int cnt = (meta[it] >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
+                                for (int c = 0; c < cnt; c++)
+                                    ez += efscale * q;                         // electricField.cu:10
+                            }
+                            if (cosine)   // cosineAccelerate.cu:9 (float += double unless double mode)
+                                ex = (real) (ex + accel * cph * vv_recip(v.w));
+                        }
+                        if (KICK == KICK_MIDDLE) {   // middle.cu:17-19
+                            v.x += stepSize * v.w * ex + fscale * v.w * fx;
+                            v.y += stepSize * v.w * ey + fscale * v.w * fy;
+                            v.z += stepSize * v.w * ez + fscale * v.w * fz;
+                        } else {                      // velocityVerlet.cu:19-21 (0.5 is a double literal)
+                            v.x += 0.5 * stepSize * v.w * ex + fscale * v.w * fx;
+                            v.y += 0.5 * stepSize * v.w * ey + fscale * v.w * fy;
+                            v.z += 0.5 * stepSize * v.w * ez + fscale * v.w * fz;
+                        }
+                    } else {
+                        // forceExtra == 0: the reference's first product is an exact zero
+                        v.x += fscale * v.w * fx;
+                        v.y += fscale * v.w * fy;
+                        v.z += fscale * v.w * fz;
+                    }
+                    st_stream(velm + idx, v);
+                }
+                vel[it] = v;
+                mixed4 sv = v;
+                sv.w = v.w != 0 ? vv_recip(v.w) : (mixed) 0;   // mass
+                st.velm[sl] = sv;
+                if (EXTRA) {
+                    st.cph[sl] = cph;
+                    if (cosine && v.w != 0)   // cosineAccelerate.cu:26
+                        acc[3] += sv.w * v.x * 2 * cph;
+                }
+            }
+        }
+        consumerBarrier();
+
+        // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), one thread per
+        //      molecule, particles in ascending order like particlesSortedByMolId -------------------
+        if (useCOM) {
+            for (int j = tid; j < nMol; j += CTHREADS) {
+                const uint32_t info = (uint32_t) st.molInfo[ml0 + j];
+                const int mol = molFirst >= 0 ? molFirst + j : p.tileMolList[m0 + j];
+                mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
+                if (!MOLINFO_SCATTERED(info)) {
+                    const int first = sl0 + MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
+                    for (int k = first; k < first + cnt; k++) {
+                        const mixed4 a = st.velm[k];
+                        if (a.w != 0) {
+                            sx += a.x * a.w; sy += a.y * a.w; sz += a.z * a.w;
+                            if (cosine) sc += st.cph[k] * a.w;
+                            comMass += a.w;
+                        }
+                    }
+                } else {
+                    const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
+                    for (int k = 0; k < cnt; k++) {
+                        const int loc = p.sortedByMol[start + k] - t0;
+                        if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
+                        const mixed4 a = st.velm[sl0 + loc];
+                        if (a.w != 0) {
+                            sx += a.x * a.w; sy += a.y * a.w; sz += a.z * a.w;
+                            if (cosine) sc += st.cph[sl0 + loc] * a.w;
+                            comMass += a.w;
+                        }
+                    }
+                }
+                mixed4 V;
+                V.w = vv_recip(comMass);
+                V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
+                sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
+                st_stream(comV + mol, V);
+                mixed cb = 0;
+                if (cosine) {
+                    cb = sc * V.w;
+                    sm.cbar[j] = cb;
+                    comCbar[mol] = cb;
+                }
+                // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w
+                acc[1] += (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
+                if (cosine) {
+                    acc[5] += comMass * V.x * cb;
+                    acc[8] += comMass * cb * cb;
+                }
+            }
+            consumerBarrier();
+        }
+
+        // ---- phase 3: group kinetic energies of the COM-normalised velocities ------------------
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const uint32_t mw = meta[it];
+            if (!(mw & VVB200_META_NH)) continue;
+            const int sl = sl0 + it * CTHREADS + tid;
+            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
+            const uint32_t lm = mw & VVB200_META_MOL_MASK;
+            mixed Vx = 0, Vy = 0, Vz = 0, cb = 0;
+            if (useCOM && lm != VVB200_META_MOL_NONE) {
+                Vx = sm.Vx[lm]; Vy = sm.Vy[lm]; Vz = sm.Vz[lm];
+                if (cosine) cb = sm.cbar[lm];
+            }
+            const mixed4 v = vel[it];
+            if (role == VVB200_ROLE_NONE) {
+                if (v.w != 0) {   // drudeNoseHoover.cu:76-83: |u|^2 / w
+                    const mixed mass = st.velm[sl].w;
+                    const mixed ux = v.x - Vx, uy = v.y - Vy, uz = v.z - Vz;
+                    acc[0] += (ux * ux + uy * uy + uz * uz) * mass;
+                    if (cosine) {
+                        const mixed d = st.cph[sl] - cb;
+                        acc[4] += ux * d * mass;
+                        acc[7] += d * d * mass;
+                    }
+                }
+            } else if (role == VVB200_ROLE_DRUDE) {   // drudeNoseHoover.cu:99-114; this thread owns the pair
+                const int psl = sl + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+                const mixed4 v2 = st.velm[psl];
+                const mixed mass1 = st.velm[sl].w, mass2 = v2.w;
+                const mixed u1x = v.x - Vx, u1y = v.y - Vy, u1z = v.z - Vz;
+                const mixed u2x = v2.x - Vx, u2y = v2.y - Vy, u2z = v2.z - Vz;
+                const mixed totalMass = mass1 + mass2;
+                const mixed invTotalMass = vv_recip(totalMass);
+                const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
+                const mixed redMass = mass1 * m2f;       // = 1 / ((m1+m2) w1 w2)
+                const mixed cmx = u1x * m1f + u2x * m2f, cmy = u1y * m1f + u2y * m2f, cmz = u1z * m1f + u2z * m2f;
+                const mixed rx = u1x - u2x, ry = u1y - u2y, rz = u1z - u2z;
+                acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
+                acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
+                if (cosine) {
+                    const mixed d1 = st.cph[sl] - cb, d2 = st.cph[psl] - cb;
+                    const mixed cmd = d1 * m1f + d2 * m2f, rd = d1 - d2;
+                    acc[4] += cmx * cmd * totalMass;
+                    acc[7] += cmd * cmd * totalMass;
+                    acc[6] += rx * rd * redMass;
+                    acc[9] += rd * rd * redMass;
+                }
+            }
+        }
+        // the tile was written through the generic proxy; order that before the next bulk copy into it
+        fenceProxyAsync();
+        mbarArrive(empty + s);
+        if (++s == stages) { s = 0; phase ^= 1; }
+    }
+
+    // ---- block reduction (fixed order), then the last block finishes ----------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        double v = (double) acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm.red[warp][k] = v;
+    }
+    consumerBarrier();
+    if (tid < VVB200_NRED) {
+        double v = 0;
+        if (tid < NR) {
+#pragma unroll
+            for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
+        }
+        p.partials[(size_t) blockIdx.x * VVB200_NRED + tid] = v;
+    }
+    __threadfence();
+    consumerBarrier();
+    if (tid == 0)
+        sm.ticket = atomicAdd(p.counter, 1u);
+    consumerBarrier();
+    if (sm.ticket != gridDim.x - 1)
+        return;
+    // last block: sum the per-block partials block-major in a fixed order
+    __threadfence();
+    for (int k = 0; k < NR; k++) {
+        double v = 0;
+        for (int b = tid; b < (int) gridDim.x; b += CTHREADS)
+            v += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm.red[warp][k] = v;
+    }
+    consumerBarrier();
+    if (tid < VVB200_NRED) {
+        double v = 0;
+        if (tid < NR)
+            for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
+        p.nhc->red[tid] = v;
+    }
+    if (tid == 0)
+        *p.counter = 0;
+    consumerBarrier();
+    if (p.fuseNHC && tid < 3) {
+        if (cosine) nhcFinish<true>(p.nhc, p.dt, tid);
+        else nhcFinish<false>(p.nhc, p.dt, tid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B: thermostat scaling + bias remove/restore + drifts + position write + hard wall
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int VARIANT, bool EXTRA> struct StageB {
+    static constexpr bool POS = VARIANT != VAR_SCALE_ONLY;
+    static constexpr bool POSQ = POS || EXTRA;
+    static constexpr bool CORR = POS && Prec<MODE>::kMixed;
+    static constexpr bool FORCE = VARIANT == VAR_VV_FIRST;
+    typename Prec<MODE>::mixed4 velm[PADT];
+    typename Prec<MODE>::mixed4 comV[MAXMOL];
+    uint32_t meta[PADT];
+    int32_t desc[8];
+    typename Prec<MODE>::real4 posq[POSQ ? PADT : 1];
+    typename Prec<MODE>::real4 corr[CORR ? PADT : 1];
+    long long f[3][FORCE ? PADT : 2];
+    typename Prec<MODE>::mixed cbar[EXTRA ? MAXMOL + 8 : 2];
+};
+
+template <int MODE, int VARIANT, bool EXTRA> constexpr size_t smemBytesB(int stages) {
+    return roundUp128(sizeof(StageB<MODE, VARIANT, EXTRA>)) * stages + 16 * stages + 128;
+}
+
+// thermostat scaling of one Drude pair (drudeNoseHoover.cu:164-208).  v* are COM-normalised (and bias-free)
+// velocities, m1f/m2f the mass fractions m_k/(m1+m2); returns the new absolute velocities.
+template <class mixed>
+__device__ __forceinline__ void scalePair(const mixed v1[3], const mixed v2[3], mixed m1f, mixed m2f, const mixed V[3],
+                                          mixed sA, mixed sC, mixed sD, mixed out1[3], mixed out2[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        mixed cm = v1[d] * m1f + v2[d] * m2f;
+        mixed rel = v2[d] - v1[d];
+        cm = sA * cm;
+        rel = sD * rel;
+        out1[d] = cm - rel * m2f + sC * V[d];
+        out2[d] = cm + rel * m1f + sC * V[d];
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void splitPos(typename Prec<MODE>::mixed x, typename Prec<MODE>::real &hi,
+                                         typename Prec<MODE>::real &lo) {
+    typedef typename Prec<MODE>::real real;
+    hi = (real) x;
+    lo = (real) (x - (typename Prec<MODE>::mixed) hi);
+}
+
+template <int MODE, int VARIANT, bool EXTRA>
+__global__ void __launch_bounds__(BTHREADS) scale_drift_kernel(const KParams p) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    typedef StageB<MODE, VARIANT, EXTRA> Stage;
+    constexpr bool POS = Stage::POS;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int stages = p.stagesB;
+    constexpr size_t stageBytes = roundUp128(sizeof(Stage));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smemRaw + stageBytes * stages);
+    uint64_t *empty = full + stages;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbarInit(full + s, 1);
+            mbarInit(empty + s, CTHREADS);
+        }
+        fenceBarrierInit();
+    }
+    __syncthreads();
+
+    const bool cosine = EXTRA && p.cosine;
+    const bool useCOM = p.useCOM;
+
+    if (tid >= CTHREADS) {
+        // ===== producer warp (all lanes stay: the gather fallback uses them) =====
+        const int lane = tid - CTHREADS;
+        const mixed4 *comV = reinterpret_cast<const mixed4 *>(p.comV);
+        const mixed *comCbar = reinterpret_cast<const mixed *>(p.comCbar);
+        int s = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+            const int4 d0 = __ldg(p.tileDesc + 2 * tile), d1 = __ldg(p.tileDesc + 2 * tile + 1);
+            mbarWait(empty + s, phase ^ 1);
+            Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+            const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
+            const int nMol = useCOM ? d0.w : 0;
+            const bool gather = nMol > 0 && d1.x < 0;
+            if (gather) {
+                // tile molecules are not consecutive ids: gather through the list (any topology)
+                for (int j = lane; j < nMol; j += 32) {
+                    const int mol = p.tileMolList[d0.z + j];
+                    st.comV[j] = comV[mol];
+                    if (cosine) st.cbar[j] = comCbar[mol];
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const int cb0 = d1.x >= 0 ? d1.x & ~3 : 0;
+                const int cbcnt = cosine && nMol > 0 && !gather ? ((d1.x + nMol + 3) & ~3) - cb0 : 0;
+                st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
+                st.desc[5] = gather ? 0 : d1.x - cb0;   // offset of this tile's first molecule in st.cbar
+                uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t));
+                if (Stage::POSQ) bytes += cnt * (uint32_t) sizeof(real4);
+                if (Stage::CORR) bytes += cnt * (uint32_t) sizeof(real4);
+                if (Stage::FORCE) bytes += 3u * cnt * 8u;
+                if (nMol > 0 && !gather) bytes += nMol * (uint32_t) sizeof(mixed4) + cbcnt * (uint32_t) sizeof(mixed);
+                mbarArriveExpectTx(full + s, bytes);
+                bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
+                bulkLoad(st.meta, p.slotMeta + a0, cnt * 4u, full + s);
+                if (Stage::POSQ) bulkLoad(st.posq, reinterpret_cast<const real4 *>(p.posq) + a0, cnt * (uint32_t) sizeof(real4), full + s);
+                if (Stage::CORR) bulkLoad(st.corr, reinterpret_cast<const real4 *>(p.corr) + a0, cnt * (uint32_t) sizeof(real4), full + s);
+                if (Stage::FORCE) {
+                    bulkLoad(st.f[0], p.force + a0, cnt * 8u, full + s);
+                    bulkLoad(st.f[1], p.force + a0 + p.paddedN, cnt * 8u, full + s);
+                    bulkLoad(st.f[2], p.force + a0 + 2 * (size_t) p.paddedN, cnt * 8u, full + s);
+                }
+                if (nMol > 0 && !gather) {
+                    bulkLoad(st.comV, comV + d1.x, nMol * (uint32_t) sizeof(mixed4), full + s);
+                    if (cbcnt) bulkLoad(st.cbar, comCbar + cb0, cbcnt * (uint32_t) sizeof(mixed), full + s);
+                }
+            }
+            if (++s == stages) { s = 0; phase ^= 1; }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
+    real4 *posq = reinterpret_cast<real4 *>(p.posq);
+    real4 *corr = reinterpret_cast<real4 *>(p.corr);
+    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
+
+    const mixed stepSize = (mixed) p.dt;
+    const mixed halfdt = 0.5f * stepSize;                       // middle.cu:33,51
+    const mixed invStepSize = (mixed) (1.0 / stepSize);         // velocityVerlet.cu:40
+    const mixed fscaleVV = (mixed) (0.5 * p.dt / (double) 0x100000000);
+    const mixed sA = (mixed) p.nhc->vscale[0], sC = (mixed) p.nhc->vscale[1], sD = (mixed) p.nhc->vscale[2];
+    const mixed Vb = cosine ? (mixed) p.nhc->vBias : (mixed) 0;
+    const mixed maxD = (mixed) p.maxDrudeDistance;
+    // conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold
+    const mixed maxD2safe = maxD * maxD * (mixed) (1.0 - 1e-4);
+    const mixed hwScale = (mixed) p.hardwallScale;
+    const real efscale = (real) p.efscale;
+    const real accel = (real) p.accel;
+    const real invBoxZ = (real) p.invBoxZ;
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        mbarWait(full + s, phase);
+        Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+        const int t0 = st.desc[0], t1 = st.desc[1], cbOff = st.desc[5];
+        const int sl0 = t0 - (t0 & ~3);
+
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * CTHREADS + tid;
+            const int idx = t0 + loc, sl = sl0 + loc;
+            if (idx >= t1) continue;
+            const uint32_t mw = st.meta[sl];
+            const mixed4 vel = st.velm[sl];
+            real4 pq;
+            pq.x = pq.y = pq.z = pq.w = 0;
+            mixed xs[3] = {0, 0, 0};
+            if (Stage::POSQ) {
+                pq = st.posq[sl];
+                xs[0] = pq.x; xs[1] = pq.y; xs[2] = pq.z;
+                if (Stage::CORR) {
+                    const real4 c = st.corr[sl];
+                    xs[0] = pq.x + (mixed) c.x;       // middle.cu:82-84
+                    xs[1] = pq.y + (mixed) c.y;
+                    xs[2] = pq.z + (mixed) c.z;
+                }
+            }
+            double cphs = 0, cq = 0;
+            if (cosine) cphs = cosPhase((double) pq.z, (double) invBoxZ);
+
+            const bool isNH = mw & VVB200_META_NH;
+            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
+            const uint32_t lm = mw & VVB200_META_MOL_MASK;
+            const int psl = sl + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+            const bool hasMol = useCOM && lm != VVB200_META_MOL_NONE;
+            mixed V[3] = {0, 0, 0};
+            mixed cb = 0;
+            if (hasMol) {
+                const mixed4 Vm = st.comV[lm];
+                V[0] = Vm.x; V[1] = Vm.y; V[2] = Vm.z;
+                if (cosine) cb = st.cbar[cbOff + lm];
+            }
+            // this particle ("s") and, for pair roles, its partner ("q")
+            mixed vs[3] = {vel.x, vel.y, vel.z};
+            const mixed ws = vel.w;
+            mixed vq[3] = {0, 0, 0}, wq = 0;
+            mixed xq[3] = {0, 0, 0};
+            real4 pqq;
+            pqq.x = pqq.y = pqq.z = pqq.w = 0;
+            if (role != VVB200_ROLE_NONE) {
+                const mixed4 v2 = st.velm[psl];
+                vq[0] = v2.x; vq[1] = v2.y; vq[2] = v2.z; wq = v2.w;
+                if (Stage::POSQ) {
+                    pqq = st.posq[psl];
+                    xq[0] = pqq.x; xq[1] = pqq.y; xq[2] = pqq.z;
+                    if (Stage::CORR) {
+                        const real4 c = st.corr[psl];
+                        xq[0] = pqq.x + (mixed) c.x; xq[1] = pqq.y + (mixed) c.y; xq[2] = pqq.z + (mixed) c.z;
+                    }
+                    if (cosine) cq = cosPhase((double) pqq.z, (double) invBoxZ);
+                }
+            }
+            // velocities entering the drift as "pre-thermostat" values (middle.cu:33-41)
+            const mixed vs0[3] = {vs[0], vs[1], vs[2]};
+            const mixed vq0[3] = {vq[0], vq[1], vq[2]};
+            bool writeVel = false;
+
+            if (isNH) {
+                // removePeriodicVelocityBias (cosineAccelerate.cu:63-71)
+                if (cosine) { vs[0] -= Vb * cphs; vq[0] -= Vb * cq; }
+                // bias-removed molecular velocity: V' = V - Vb*cbar e_x
+                mixed Vn[3] = {V[0], V[1], V[2]};
+                if (cosine && hasMol) Vn[0] = V[0] - Vb * cb;
+                if (hasMol) {   // normalizeVelocities, drudeNoseHoover.cu:42-48
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { vs[d] -= Vn[d]; vq[d] -= Vn[d]; }
+                }
+                if (role == VVB200_ROLE_NONE) {
+                    if (ws != 0) {
+#pragma unroll
+                        for (int d = 0; d < 3; d++) vs[d] = sA * vs[d] + sC * Vn[d];   // drudeNoseHoover.cu:172-176
+                    }
+                    writeVel = cosine || hasMol || ws != 0;
+                } else {
+                    // mass fractions m_k/(m1+m2) = w_other/(w1+w2): one division per pair member
+                    const mixed invW = vv_recip(ws + wq);
+                    const mixed fs = wq * invW, fq = ws * invW;
+                    mixed o1[3], o2[3];
+                    if (role == VVB200_ROLE_DRUDE) {
+                        scalePair<mixed>(vs, vq, fs, fq, Vn, sA, sC, sD, o1, o2);
+#pragma unroll
+                        for (int d = 0; d < 3; d++) { vs[d] = o1[d]; vq[d] = o2[d]; }
+                    } else {
+                        scalePair<mixed>(vq, vs, fq, fs, Vn, sA, sC, sD, o1, o2);
+#pragma unroll
+                        for (int d = 0; d < 3; d++) { vq[d] = o1[d]; vs[d] = o2[d]; }
+                    }
+                    writeVel = true;
+                }
+                if (cosine) { vs[0] += Vb * cphs; vq[0] += Vb * cq; }   // restorePeriodicVelocityBias
+            } else if (cosine) {
+                // non-thermostatted atoms still see remove then restore (cosineAccelerate.cu:63-84)
+                vs[0] -= Vb * cphs; vs[0] += Vb * cphs;
+                vq[0] -= Vb * cq; vq[0] += Vb * cq;
+                writeVel = true;
+            }
+
+            if (VARIANT == VAR_SCALE_ONLY) {
+                if (writeVel) {
+                    mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                    st_stream(velm + idx, o);
+                }
+                continue;
+            }
+
+            bool writePos = false;
+            if (VARIANT == VAR_VV_FIRST) {
+                // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
+                // particle and (redundantly) its partner
+                for (int who = 0; who < 2; who++) {
+                    if (who == 1 && role == VVB200_ROLE_NONE) break;
+                    const int js = who == 0 ? sl : psl;
+                    mixed *v = who == 0 ? vs : vq;
+                    const mixed w = who == 0 ? ws : wq;
+                    if (w == 0) continue;
+                    real ex = 0, ey = 0, ez = 0;
+                    if (EXTRA && p.extraForces) {
+                        const uint32_t mj = who == 0 ? mw : st.meta[js];
+                        if (p.hasLD && (mj & VVB200_META_LD)) {
+                            const real3 f = ldForce[p.ldSlot[t0 + js - sl0]];
+                            ex = f.x; ey = f.y; ez = f.z;
+                        }
+                        if (p.hasField) {
+                            const int cnt = (mj >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
+                            const real q = who == 0 ? pq.w : pqq.w;
+                            for (int c = 0; c < cnt; c++) ez += efscale * q;
+                        }
+                        if (cosine) {
+                            const double c = who == 0 ? cphs : cq;
+                            ex = (real) (ex + accel * c * vv_recip(w));
+                        }
+                    }
+                    const long long fx = st.f[0][Stage::FORCE ? js : 0], fy = st.f[1][Stage::FORCE ? js : 0],
+                                    fz = st.f[2][Stage::FORCE ? js : 0];
+                    v[0] += 0.5 * stepSize * w * ex + fscaleVV * w * fx;
+                    v[1] += 0.5 * stepSize * w * ey + fscaleVV * w * fy;
+                    v[2] += 0.5 * stepSize * w * ez + fscaleVV * w * fz;
+                }
+                // posDelta = dt*v ; x += posDelta ; v = posDelta/dt  (velocityVerlet.cu:25,52-58)
+                if (ws != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const mixed delta = stepSize * vs[d];
+                        xs[d] += delta;
+                        vs[d] = (mixed) (invStepSize * delta);
+                    }
+                    writePos = writeVel = true;
+                }
+                if (role != VVB200_ROLE_NONE && wq != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const mixed delta = stepSize * vq[d];
+                        xq[d] += delta;
+                        vq[d] = (mixed) (invStepSize * delta);
+                    }
+                }
+            } else {
+                // middle scheme without constraints: posDelta = oldDelta = halfdt*v0 + halfdt*v', so
+                // integrateMiddlePos3 leaves v' unchanged and moves x by posDelta (middle.cu:33-98)
+                if (ws != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        mixed delta = halfdt * vs0[d];
+                        delta += halfdt * vs[d];
+                        xs[d] += delta;
+                    }
+                    writePos = writeVel = true;
+                }
+                if (role != VVB200_ROLE_NONE && wq != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        mixed delta = halfdt * vq0[d];
+                        delta += halfdt * vq[d];
+                        xq[d] += delta;
+                    }
+                }
+            }
+
+            // ---- Drude hard wall (middle.cu:114-220), evaluated by both members of the pair ----------
+            if (p.hardwall && role != VVB200_ROLE_NONE) {
+                // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
+                if (P::kMixed) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        real hi, lo;
+                        if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
+                        if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
+                    }
+                }
+                const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
+                mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
+                const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
+                const mixed d2 = dx * dx + dy * dy + dz * dz;
+                if (!(d2 < maxD2safe)) {
+                    mixed *vel1 = selfIsDrude ? vs : vq, *vel2 = selfIsDrude ? vq : vs;
+                    const mixed w1 = selfIsDrude ? ws : wq, w2 = selfIsDrude ? wq : ws;
+                    const mixed r = vv_sqrt<MODE, mixed>(d2);
+                    const mixed rInv = vv_recip(r);
+                    if (rInv * maxD < 1) {
+                        const mixed bond[3] = {dx * rInv, dy * rInv, dz * rInv};
+                        const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
+                        const mixed deltaR = r - maxD;
+                        mixed deltaT = stepSize;
+                        mixed dotvr1 = vel1[0] * bond[0] + vel1[1] * bond[1] + vel1[2] * bond[2];
+                        mixed vp1[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) vp1[d] = vel1[d] - bond[d] * dotvr1;
+                        if (w2 == 0) {
+                            if (dotvr1 != 0) deltaT = deltaR / fabs(dotvr1);
+                            if (deltaT > stepSize) deltaT = stepSize;
+                            dotvr1 = -dotvr1 * hwScale / (fabs(dotvr1) * vv_sqrt<MODE, mixed>(mass1));
+                            const mixed dr = -deltaR + deltaT * dotvr1;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                pos1[d] += bond[d] * dr;
+                                vel1[d] = vp1[d] + bond[d] * dotvr1;
+                            }
+                        } else {
+                            const mixed invTotalMass = vv_recip(mass1 + mass2);
+                            mixed dotvr2 = vel2[0] * bond[0] + vel2[1] * bond[1] + vel2[2] * bond[2];
+                            mixed vp2[3];
+#pragma unroll
+                            for (int d = 0; d < 3; d++) vp2[d] = vel2[d] - bond[d] * dotvr2;
+                            const mixed vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
+                            dotvr1 -= vbCMass;
+                            dotvr2 -= vbCMass;
+                            if (dotvr1 != dotvr2) deltaT = deltaR / fabs(dotvr1 - dotvr2);
+                            if (deltaT > stepSize) deltaT = stepSize;
+                            const mixed vBond = hwScale / vv_sqrt<MODE, mixed>(mass1);
+                            dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabs(dotvr1);
+                            dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabs(dotvr2);
+                            const mixed dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
+                            const mixed dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
+                            dotvr1 += vbCMass;
+                            dotvr2 += vbCMass;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                pos1[d] += bond[d] * dr1;
+                                pos2[d] += bond[d] * dr2;
+                                vel1[d] = vp1[d] + bond[d] * dotvr1;
+                                vel2[d] = vp2[d] + bond[d] * dotvr2;
+                            }
+                        }
+                        // the reference writes the touched members unconditionally (middle.cu:166-172, 204-219)
+                        if (selfIsDrude || w2 != 0) writePos = writeVel = true;
+                    }
+                }
+            }
+
+            if (writeVel) {
+                mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                st_stream(velm + idx, o);
+            }
+            if (POS && writePos) {
+                real4 o;
+                if (P::kMixed) {
+                    real4 oc;
+                    splitPos<MODE>(xs[0], o.x, oc.x);
+                    splitPos<MODE>(xs[1], o.y, oc.y);
+                    splitPos<MODE>(xs[2], o.z, oc.z);
+                    o.w = pq.w;
+                    oc.w = 0;
+                    st_stream(posq + idx, o);
+                    st_stream(corr + idx, oc);
+                } else {
+                    o.x = (real) xs[0]; o.y = (real) xs[1]; o.z = (real) xs[2]; o.w = pq.w;
+                    st_stream(posq + idx, o);
+                }
+            }
+        }
+        mbarArrive(empty + s);   // this thread is done reading the stage
+        if (++s == stages) { s = 0; phase ^= 1; }
+    }
+}
