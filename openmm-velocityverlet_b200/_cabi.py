@@ -112,7 +112,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("VVB200_LIB") or LIB_PATH      # VVB200_LIB: tuning builds of the same ABI
     if not os.path.exists(path):
         raise VVB200Error(6, f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                              f"(there is no CPU fallback)")
@@ -154,7 +154,7 @@ def load_library(path=None):
     lib.vvb200_step_host.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, vp]
     lib.vvb200_profile_enable.argtypes = [vp, C.c_int]
     lib.vvb200_profile_read.argtypes = [vp, P(dbl), P(dbl), P(i32)]
-    if path == LIB_PATH:
+    if path in (LIB_PATH, os.environ.get("VVB200_LIB")):
         _lib = lib
     return lib
 

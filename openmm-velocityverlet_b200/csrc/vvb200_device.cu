@@ -36,7 +36,7 @@
 #define AVOGADRO_D 6.02214076e23
 
 #define THREADS 256                       // block size of the small element-wise kernels
-#define VVB200_MAX_BLOCKS_PER_SM 4
+#define VVB200_MAX_BLOCKS_PER_SM 8
 
 // ------------------------------------------------------------------------------------------------
 // precision traits: OpenMM's CudaPrecision modes
@@ -737,8 +737,9 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
 }
 
 // Persistent launch geometry: blocksPerSM co-resident blocks per SM (148 SMs), each with a ring of `stages`
-// shared-memory stages, striding over the molecule-aligned tiles.  Defaults: two blocks per SM, as many stages
-// as fit the 227 KB of shared memory (at least 2); VVB200_STAGES_A/B and VVB200_BLOCKS_PER_SM override (tuning).
+// shared-memory stages, striding over the molecule-aligned tiles.  Defaults: MINBLOCKS_A / MINBLOCKS_B blocks per SM
+// (what the kernels' __launch_bounds__ were compiled for) and as many stages as then fit the 227 KB of shared
+// memory; VVB200_STAGES_A/B and VVB200_BLOCKS_A/B override (tuning).
 static int envInt(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -747,16 +748,16 @@ static int envInt(const char *name, int dflt) {
 struct LaunchCfg { int stages, perSM; size_t smem; };
 
 template <class F>
-static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stagesEnv, int numSM) {
+static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stagesEnv, const char *blocksEnv, int dfltBlocks) {
     int dev = 0, maxOptin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     LaunchCfg c;
-    c.perSM = std::max(1, std::min(envInt("VVB200_BLOCKS_PER_SM", 2), VVB200_MAX_BLOCKS_PER_SM));
+    c.perSM = std::max(1, std::min(envInt(blocksEnv, dfltBlocks), VVB200_MAX_BLOCKS_PER_SM));
     const size_t perSMBudget = 227 * 1024;
     int stages = envInt(stagesEnv, 0);
     if (stages <= 0) {
-        stages = 2;
+        stages = 1;
         while (stages < 8 && (smemBytes(stages + 1) + 1024) * c.perSM <= perSMBudget) stages++;
     }
     while (stages > 1 && smemBytes(stages) > (size_t) maxOptin) stages--;
@@ -766,13 +767,12 @@ static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stage
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BTHREADS, c.smem);
     c.perSM = std::max(1, std::min(c.perSM, occ));
-    (void) numSM;
     return c;
 }
 
 template <int MODE, int KICK, bool EXTRA>
 static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
-    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", numSM);
+    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", MINBLOCKS_A);
     k.stagesA = cfg.stages;
     const int grid = std::max(1, std::min(k.numTiles, numSM * cfg.perSM));
     kick_reduce_kernel<MODE, KICK, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
@@ -781,7 +781,7 @@ static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
 
 template <int MODE, int VARIANT, bool EXTRA>
 static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
-    static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", numSM);
+    static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", MINBLOCKS_B);
     k.stagesB = cfg.stages;
     const int grid = std::max(1, std::min(k.numTiles, numSM * cfg.perSM));
     scale_drift_kernel<MODE, VARIANT, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);

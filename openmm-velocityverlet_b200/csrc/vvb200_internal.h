@@ -33,7 +33,9 @@
 #define VVB200_ROLE_PARENT 2u
 
 // particles per tile of the fused kernels (threads x items); must be <= 1024 (11-bit local ids)
+#ifndef VVB200_TILE_CAP
 #define VVB200_TILE_CAP 512
+#endif
 // thermostat molecules per tile (bounds the per-stage molecule tables of the fused kernels)
 #define VVB200_TILE_MAX_MOLS 128
 

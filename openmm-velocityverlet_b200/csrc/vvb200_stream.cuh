@@ -17,8 +17,16 @@
 // copied for the slot range [t0 & ~3, roundup4(t1)) and consumers index with the offset t0 - (t0 & ~3).
 #pragma once
 
+#ifndef CTHREADS
 #define CTHREADS 256                          // consumer threads
+#endif
 #define BTHREADS (CTHREADS + 32)              // + one producer warp
+#ifndef MINBLOCKS_A
+#define MINBLOCKS_A 3                         // pass A: 3 co-resident blocks (<= 72 registers) hide its block barriers
+#endif
+#ifndef MINBLOCKS_B
+#define MINBLOCKS_B 2
+#endif
 #define ITEMS (VVB200_TILE_CAP / CTHREADS)
 #define PADT (VVB200_TILE_CAP + 8)            // stage slots: tile + alignment slack
 #define MAXMOL VVB200_TILE_MAX_MOLS
@@ -61,17 +69,27 @@ __device__ __forceinline__ void consumerBarrier() { asm volatile("bar.sync 1, %0
 // molFirst >= 0: the tile's thermostat molecules are the consecutive ids molFirst .. molFirst+nMol-1
 
 template <int MODE, bool EXTRA> struct StageA {
-    typename Prec<MODE>::mixed4 velm[PADT];      // consumers overwrite it with (v', mass)
+    typename Prec<MODE>::mixed4 velm[PADT];
     long long f[3][PADT];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
     int32_t desc[8];
     typename Prec<MODE>::real4 posq[EXTRA ? PADT : 1];
-    double cph[EXTRA ? PADT : 2];
+};
+
+// what phase 1 publishes for the molecule and pair phases: kicked velocities and masses as a structure of
+// arrays (conflict-free shared-memory access), double-buffered so that the next tile's phase 1 may start while
+// slow warps still read this tile's.  The TMA stage itself is released right after phase 1.
+template <int MODE, bool EXTRA> struct PublishedA {
+    typedef typename Prec<MODE>::mixed mixed;
+    mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], m[VVB200_TILE_CAP];
+    double cph[EXTRA ? VVB200_TILE_CAP : 2];
+    int32_t molInfo[MAXMOL];
 };
 
 template <int MODE, bool EXTRA> struct ScratchA {
     typedef typename Prec<MODE>::mixed mixed;
+    PublishedA<MODE, EXTRA> pub[2];
     mixed Vx[MAXMOL], Vy[MAXMOL], Vz[MAXMOL];
     mixed cbar[EXTRA ? MAXMOL : 1];
     double red[CTHREADS / 32][VVB200_NRED];
@@ -84,11 +102,14 @@ template <int MODE, bool EXTRA> constexpr size_t smemBytesA(int stages) {
     return roundUp128(sizeof(StageA<MODE, EXTRA>)) * stages + roundUp128(sizeof(ScratchA<MODE, EXTRA>)) + 16 * stages + 128;
 }
 
+// lanes that cooperate on one molecule's centre of mass
+#define COM_LANES 8
+
 // ------------------------------------------------------------------------------------------------
 // pass A: extra forces + kick + molecular COM + group kinetic energies (+ bias moments) + NH chains
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int KICK, bool EXTRA>
-__global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) {
+__global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(const KParams p) {
     typedef Prec<MODE> P;
     typedef typename P::real real;
     typedef typename P::mixed mixed;
@@ -168,17 +189,18 @@ __global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) 
 #pragma unroll
     for (int k = 0; k < NR; k++) acc[k] = 0;
 
-    int s = 0;
+    int s = 0, buf = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
-        const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = st.desc[3], molFirst = st.desc[4];
+        PublishedA<MODE, EXTRA> &pub = sm.pub[buf];
+        const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
         const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
 
-        mixed4 vel[ITEMS];
+        mixed4 vel[ITEMS];       // .w holds the MASS from here on (0 for massless)
         uint32_t meta[ITEMS];
-        // ---- phase 1: extra forces, kick, store; publish (v', mass) to the tile ---------------------
+        // ---- phase 1: extra forces, kick, store; publish v' and mass --------------------------------
 #pragma unroll
         for (int it = 0; it < ITEMS; it++) {
             const int loc = it * CTHREADS + tid;
@@ -230,65 +252,82 @@ __global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) 
                     }
                     st_stream(velm + idx, v);
                 }
+                const mixed mass = v.w != 0 ? vv_recip(v.w) : (mixed) 0;
                 vel[it] = v;
-                mixed4 sv = v;
-                sv.w = v.w != 0 ? vv_recip(v.w) : (mixed) 0;   // mass
-                st.velm[sl] = sv;
+                vel[it].w = mass;
+                pub.vx[loc] = v.x; pub.vy[loc] = v.y; pub.vz[loc] = v.z; pub.m[loc] = mass;
                 if (EXTRA) {
-                    st.cph[sl] = cph;
+                    pub.cph[loc] = cph;
                     if (cosine && v.w != 0)   // cosineAccelerate.cu:26
-                        acc[3] += sv.w * v.x * 2 * cph;
+                        acc[3] += mass * v.x * 2 * cph;
                 }
             }
         }
+        if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
+        mbarArrive(empty + s);      // this thread no longer needs the stage: the producer may refill it
+        if (++s == stages) { s = 0; phase ^= 1; }
         consumerBarrier();
 
-        // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), one thread per
-        //      molecule, particles in ascending order like particlesSortedByMolId -------------------
-        if (useCOM) {
-            for (int j = tid; j < nMol; j += CTHREADS) {
-                const uint32_t info = (uint32_t) st.molInfo[ml0 + j];
-                const int mol = molFirst >= 0 ? molFirst + j : p.tileMolList[m0 + j];
+        // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30): COM_LANES lanes per
+        //      molecule stride over its particles, then a butterfly over the lane group (fixed order) ----
+        if (nMol > 0) {
+            const int grp = tid / COM_LANES, sub = tid % COM_LANES;
+            for (int jb = 0; jb < nMol; jb += CTHREADS / COM_LANES) {
+                const int j = jb + grp;
+                const bool active = j < nMol;
                 mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
-                if (!MOLINFO_SCATTERED(info)) {
-                    const int first = sl0 + MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
-                    for (int k = first; k < first + cnt; k++) {
-                        const mixed4 a = st.velm[k];
-                        if (a.w != 0) {
-                            sx += a.x * a.w; sy += a.y * a.w; sz += a.z * a.w;
-                            if (cosine) sc += st.cph[k] * a.w;
-                            comMass += a.w;
+                uint32_t info = 0;
+                int mol = 0;
+                if (active) {
+                    info = (uint32_t) pub.molInfo[j];
+                    mol = molFirst >= 0 ? molFirst + j : p.tileMolList[m0 + j];
+                    if (!MOLINFO_SCATTERED(info)) {
+                        const int first = MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
+                        for (int k = first + sub; k < first + cnt; k += COM_LANES) {
+                            const mixed mass = pub.m[k];        // 0 for massless particles: no contribution
+                            sx += pub.vx[k] * mass; sy += pub.vy[k] * mass; sz += pub.vz[k] * mass;
+                            if (cosine) sc += pub.cph[k] * mass;
+                            comMass += mass;
                         }
-                    }
-                } else {
-                    const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
-                    for (int k = 0; k < cnt; k++) {
-                        const int loc = p.sortedByMol[start + k] - t0;
-                        if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
-                        const mixed4 a = st.velm[sl0 + loc];
-                        if (a.w != 0) {
-                            sx += a.x * a.w; sy += a.y * a.w; sz += a.z * a.w;
-                            if (cosine) sc += st.cph[sl0 + loc] * a.w;
-                            comMass += a.w;
+                    } else if (sub == 0) {
+                        // members interleaved with other molecules: walk the sorted list (any topology)
+                        const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
+                        for (int k = 0; k < cnt; k++) {
+                            const int loc = p.sortedByMol[start + k] - t0;
+                            if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
+                            const mixed mass = pub.m[loc];
+                            sx += pub.vx[loc] * mass; sy += pub.vy[loc] * mass; sz += pub.vz[loc] * mass;
+                            if (cosine) sc += pub.cph[loc] * mass;
+                            comMass += mass;
                         }
                     }
                 }
-                mixed4 V;
-                V.w = vv_recip(comMass);
-                V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
-                sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
-                st_stream(comV + mol, V);
-                mixed cb = 0;
-                if (cosine) {
-                    cb = sc * V.w;
-                    sm.cbar[j] = cb;
-                    comCbar[mol] = cb;
+#pragma unroll
+                for (int off = COM_LANES / 2; off > 0; off >>= 1) {
+                    sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, off);
+                    sz += __shfl_xor_sync(0xffffffffu, sz, off);
+                    comMass += __shfl_xor_sync(0xffffffffu, comMass, off);
+                    if (EXTRA) sc += __shfl_xor_sync(0xffffffffu, sc, off);
                 }
-                // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w
-                acc[1] += (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
-                if (cosine) {
-                    acc[5] += comMass * V.x * cb;
-                    acc[8] += comMass * cb * cb;
+                if (active && sub == 0) {
+                    mixed4 V;
+                    V.w = vv_recip(comMass);
+                    V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
+                    sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
+                    st_stream(comV + mol, V);
+                    mixed cb = 0;
+                    if (cosine) {
+                        cb = sc * V.w;
+                        sm.cbar[j] = cb;
+                        comCbar[mol] = cb;
+                    }
+                    // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w
+                    acc[1] += (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
+                    if (cosine) {
+                        acc[5] += comMass * V.x * cb;
+                        acc[8] += comMass * cb * cb;
+                    }
                 }
             }
             consumerBarrier();
@@ -299,7 +338,7 @@ __global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) 
         for (int it = 0; it < ITEMS; it++) {
             const uint32_t mw = meta[it];
             if (!(mw & VVB200_META_NH)) continue;
-            const int sl = sl0 + it * CTHREADS + tid;
+            const int loc = it * CTHREADS + tid;
             const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
             const uint32_t lm = mw & VVB200_META_MOL_MASK;
             mixed Vx = 0, Vy = 0, Vz = 0, cb = 0;
@@ -307,24 +346,22 @@ __global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) 
                 Vx = sm.Vx[lm]; Vy = sm.Vy[lm]; Vz = sm.Vz[lm];
                 if (cosine) cb = sm.cbar[lm];
             }
-            const mixed4 v = vel[it];
+            const mixed4 v = vel[it];     // .w = mass
             if (role == VVB200_ROLE_NONE) {
                 if (v.w != 0) {   // drudeNoseHoover.cu:76-83: |u|^2 / w
-                    const mixed mass = st.velm[sl].w;
                     const mixed ux = v.x - Vx, uy = v.y - Vy, uz = v.z - Vz;
-                    acc[0] += (ux * ux + uy * uy + uz * uz) * mass;
+                    acc[0] += (ux * ux + uy * uy + uz * uz) * v.w;
                     if (cosine) {
-                        const mixed d = st.cph[sl] - cb;
-                        acc[4] += ux * d * mass;
-                        acc[7] += d * d * mass;
+                        const mixed d = pub.cph[loc] - cb;
+                        acc[4] += ux * d * v.w;
+                        acc[7] += d * d * v.w;
                     }
                 }
             } else if (role == VVB200_ROLE_DRUDE) {   // drudeNoseHoover.cu:99-114; this thread owns the pair
-                const int psl = sl + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-                const mixed4 v2 = st.velm[psl];
-                const mixed mass1 = st.velm[sl].w, mass2 = v2.w;
+                const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+                const mixed mass1 = v.w, mass2 = pub.m[ploc];
                 const mixed u1x = v.x - Vx, u1y = v.y - Vy, u1z = v.z - Vz;
-                const mixed u2x = v2.x - Vx, u2y = v2.y - Vy, u2z = v2.z - Vz;
+                const mixed u2x = pub.vx[ploc] - Vx, u2y = pub.vy[ploc] - Vy, u2z = pub.vz[ploc] - Vz;
                 const mixed totalMass = mass1 + mass2;
                 const mixed invTotalMass = vv_recip(totalMass);
                 const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
@@ -334,7 +371,7 @@ __global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) 
                 acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
                 acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
                 if (cosine) {
-                    const mixed d1 = st.cph[sl] - cb, d2 = st.cph[psl] - cb;
+                    const mixed d1 = pub.cph[loc] - cb, d2 = pub.cph[ploc] - cb;
                     const mixed cmd = d1 * m1f + d2 * m2f, rd = d1 - d2;
                     acc[4] += cmx * cmd * totalMass;
                     acc[7] += cmd * cmd * totalMass;
@@ -343,10 +380,7 @@ __global__ void __launch_bounds__(BTHREADS) kick_reduce_kernel(const KParams p) 
                 }
             }
         }
-        // the tile was written through the generic proxy; order that before the next bulk copy into it
-        fenceProxyAsync();
-        mbarArrive(empty + s);
-        if (++s == stages) { s = 0; phase ^= 1; }
+        buf ^= 1;
     }
 
     // ---- block reduction (fixed order), then the last block finishes ----------------------------
@@ -449,7 +483,7 @@ __device__ __forceinline__ void splitPos(typename Prec<MODE>::mixed x, typename 
 }
 
 template <int MODE, int VARIANT, bool EXTRA>
-__global__ void __launch_bounds__(BTHREADS) scale_drift_kernel(const KParams p) {
+__global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(const KParams p) {
     typedef Prec<MODE> P;
     typedef typename P::real real;
     typedef typename P::mixed mixed;
