@@ -14,7 +14,6 @@ N x 16.4M particles partitioned by whole molecules), mixed precision, temperatur
 JSON keys beyond the base contract are documented in DESIGN.md (section "Measurement").
 """
 import argparse
-import ctypes as C
 import json
 import os
 import sys
@@ -110,7 +109,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.nv is not None:
@@ -195,14 +194,6 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-class _DevPtr:
-    """zero-copy torch view of a raw device pointer (the plan's fp64 reduction vector)"""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False),
-                                         "version": 3, "strides": None}
-
-
 def pinned_state(vv, host):
     """copy a HostState into page-locked memory (torch is the allocator)"""
     import torch
@@ -248,28 +239,19 @@ def main():
     spec = vv.make_bulk_ionic_liquid(args.ion_pairs)
     params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
     host = vv.make_state(spec, args.precision, seed=12345 + 100 * rank, force_sigma=FORCE_SIGMA)
-    plan = vv.Plan(spec, params, args.precision)
-    if world > 1:
-        # this rank holds one whole-molecule partition of a box `world` times larger: thermostat DOFs and the
-        # total mass are those of the whole box (every partition has the same topology here)
-        plan.set_global_thermostat(plan.f64_array("dof") * world, world / plan.f64_array("invMassTotal")[0])
-    plan.upload()
+    # this rank holds one whole-molecule partition of a box `world` times larger: DistributedPlan all-reduces the
+    # thermostat DOFs and the total mass of the whole box at set-up (world == 1: the plan's own)
+    dplan = vv.DistributedPlan(spec, params, args.precision).upload()
+    plan = dplan.plan
     bufs = vv.DeviceBuffers(host)
     n_local = spec.n
     stream = torch.cuda.current_stream()
 
-    red = None
-    if world > 1:
-        ptr, cnt = plan.partials()
-        red = torch.as_tensor(_DevPtr(ptr, cnt), device="cuda")
-
     def one_step():
         if world == 1:
-            plan.step_middle(bufs)
+            plan.step_middle(bufs)                     # pass A (NH chains in its last block) + pass B
         else:
-            plan.middle_kick_reduce(bufs)
-            dist.all_reduce(red)                       # <= 10 doubles over NVLink (the only exchange)
-            plan.middle_nhc_scale_drift(bufs)
+            dplan.step_middle(bufs)                    # pass A, all-reduce of <= 10 doubles over NVLink, NHC + pass B
 
     def barrier():
         if world > 1:

@@ -143,7 +143,8 @@ enum {
     VVB200_F64_DOF,                     /* tempGroupDof[3], CudaVVKernels.cpp:497-564 */
     VVB200_F64_ETA_MASS,                /* etaMass[numTempGroup][numNHChains], :583-594 */
     VVB200_F64_NKBT,                    /* tempGroupNkbT[numTempGroup] */
-    VVB200_F64_INV_MASS_TOTAL           /* invMassTotal, :1028-1031 */
+    VVB200_F64_INV_MASS_TOTAL,          /* invMassTotal, :1028-1031 */
+    VVB200_F64_DOF_GLOBAL               /* new: whole-box DOFs[3] set by vvb200_set_global_thermostat */
 };
 int vvb200_plan_get_f64_array(const vvb200_plan *plan, int which, const double **ptr, int64_t *len);
 int vvb200_plan_num_temp_groups(const vvb200_plan *plan);

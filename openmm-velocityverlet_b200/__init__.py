@@ -29,3 +29,4 @@ from .system import (  # noqa: F401
     np_dtypes,
 )
 from .buffers import DeviceBuffers  # noqa: F401
+from .multigpu import DistributedPlan, global_thermostat, partition_by_molecules  # noqa: F401

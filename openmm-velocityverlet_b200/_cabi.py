@@ -16,7 +16,7 @@ INT_ARRAYS = {
     "particlesInMolecules": 5, "normalNH": 6, "pairsNH": 7, "normalLD": 8, "pairsLD": 9,
     "imagePairs": 10, "electrolyte": 11, "tileStart": 12, "slotMeta": 13,
 }
-F64_ARRAYS = {"moleculeMasses": 0, "moleculeInvMasses": 1, "dof": 2, "etaMass": 3, "NkbT": 4, "invMassTotal": 5}
+F64_ARRAYS = {"moleculeMasses": 0, "moleculeInvMasses": 1, "dof": 2, "etaMass": 3, "NkbT": 4, "invMassTotal": 5, "dofGlobal": 6}
 
 
 class VVB200Error(RuntimeError):

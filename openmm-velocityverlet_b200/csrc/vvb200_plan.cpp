@@ -504,6 +504,7 @@ extern "C" int vvb200_plan_get_f64_array(const vvb200_plan *p, int which, const 
     case VVB200_F64_ETA_MASS: *ptr = p->etaMass.data(); *len = (int64_t) p->etaMass.size(); break;
     case VVB200_F64_NKBT: *ptr = p->NkbT.data(); *len = (int64_t) p->NkbT.size(); break;
     case VVB200_F64_INV_MASS_TOTAL: *ptr = &p->invMassTotal; *len = 1; break;
+    case VVB200_F64_DOF_GLOBAL: *ptr = p->dofGlobal; *len = 3; break;
     default:
         vvb200_set_error("vvb200_plan_get_f64_array: unknown array id %d", which);
         return VVB200_ERR_INVALID_ARGUMENT;

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""N-GPU parity check of the molecule-partitioned path (not collected by pytest; run under torchrun on a box with
+>= 2 GPUs):   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+                     --master-port 29511 tests/multigpu_check.py
+Every rank steps its whole-molecule partition with DistributedPlan (kick_reduce -> NCCL all-reduce of 10 doubles ->
+nhc_scale_drift); rank 0 also steps the WHOLE system on its own GPU with the fused single-GPU path and compares:
+positions / velocities of its partition and the thermostat state must agree to fp64 reassociation (1e-11)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as entry  # noqa: E402
+from conftest import rel_err  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    vv = entry.load_package()
+    steps = 5
+    for name, spec, params, kw in (
+            ("bulk", vv.make_bulk_ionic_liquid(3000, has_cmm=True), vv.Params(max_drude_distance=0.02), {}),
+            ("bulk+cos", vv.make_bulk_ionic_liquid(1500), vv.Params(max_drude_distance=0.02, cos_acceleration=0.02), dict(cos=True)),
+            ("nonpolar", vv.make_nonpolar_box(5000, 8), vv.Params(), {})):
+        params = params.resolved_for(spec)
+        host = vv.make_state(spec, "mixed")
+        inv_box_z = 1.0 / host.box[2] if kw.get("cos") else 0.0
+        a, b = vv.partition_by_molecules(spec, world)[rank]
+        local_spec = spec.subset_molecules(a, b)
+        P = local_spec.padded_n
+
+        def cut(x):
+            out = np.zeros((P,) + x.shape[1:], x.dtype)
+            out[: b - a] = x[a:b]
+            return out
+        lf = np.zeros((3, P), np.int64)
+        lf[:, : b - a] = host.force[:, a:b]
+        lstate = vv.HostState("mixed", cut(host.posq), cut(host.corr), cut(host.velm), lf, host.random, host.box)
+        dp = vv.DistributedPlan(local_spec, params, "mixed").upload()
+        bufs = vv.DeviceBuffers(lstate)
+        for _ in range(steps):
+            dp.step_middle(bufs, inv_box_z=inv_box_z)
+        got = bufs.to_host()
+        st = dp.plan.thermostat_state()
+        ok = True
+        if rank == 0:
+            full = vv.Plan(spec, params, "mixed").upload()
+            fb = vv.DeviceBuffers(host)
+            full.step(fb, steps=steps, inv_box_z=inv_box_z)
+            want = fb.to_host()
+            sw = full.thermostat_state()
+            ev = rel_err(got.velm[: b - a, :3], want.velm[a:b, :3])
+            ex = rel_err(got.positions()[: b - a], want.positions()[a:b])
+            ek = rel_err(st["ke2"], sw["ke2"])
+            es = rel_err(st["vscale"], sw["vscale"])
+            ok = max(ev, ex) < 1e-9 and max(ek, es) < 1e-12
+            print(f"[{name}] world={world} N={spec.n}: v {ev:.2e} x {ex:.2e} ke2 {ek:.2e} vscale {es:.2e} "
+                  f"bias {st['velocity_bias']:.6e}/{sw['velocity_bias']:.6e} -> {'OK' if ok else 'FAIL'}", flush=True)
+        # scale factors identical on every rank
+        t = torch.tensor(st["vscale"], device="cuda", dtype=torch.float64)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        same = all(torch.equal(x, g[0]) for x in g)
+        if rank == 0:
+            print(f"[{name}] scale factors bitwise identical across ranks: {same}", flush=True)
+        flag = torch.tensor([int(ok and same)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() != 1:
+            dist.destroy_process_group()
+            sys.exit(1)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("multigpu_check: all OK")
+
+
+if __name__ == "__main__":
+    main()
