@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: min(steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     return ap.parse_args()
 
@@ -356,6 +357,29 @@ def main():
                "api": "vvb200_step_host (pinned host buffers)" if world == 1 else
                       "Plan.middle_kick_reduce + NCCL all-reduce + Plan.middle_nhc_scale_drift with pinned H2D/D2H"}
 
+    # ---- the reference's own CUDA kernels on this GPU (rank 0, single-GPU runs; reported, not the headline) ------
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_ref_gpu:
+        vo = entry.load_oracle()
+        if vo.ref_available(args.precision, gpu=True):
+            oracle = vo.Oracle(spec, params, args.precision, literal=False)     # supplies the index arrays only
+            ref = vo.Reference(oracle, gpu=True)
+            rb = vv.DeviceBuffers(host)
+            ref.step(rb, steps=2)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ksteps = 5
+            r0.record(stream)
+            nl = ref.step(rb, steps=ksteps)
+            r1.record(stream)
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1) / ksteps
+            ref_gpu = {"what": "reference kernels (platforms/cuda/src/kernels/*.cu, unmodified) compiled for sm_100a, "
+                               "OpenMM launch geometry, blocking D2H/H2D around the host NH chain (oracle/_ref)",
+                       "ms_per_step": rms, "value": n_local / (rms * 1e-3), "unit": UNIT,
+                       "launches_per_step": nl / ksteps, "speedup_device_resident": rms / ms_per_step}
+            del ref, rb, oracle
+
     # ---- CPU baseline (rank 0, single-GPU runs only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -372,6 +396,7 @@ def main():
                            "l2": "inputs larger than L2 (1.4 GB of state per GPU vs 126 MB)",
                            "parallelism": f"molecule-partitioned x{world}" if world > 1 else "single GPU"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "reference_kernels_on_gpu": ref_gpu,
                 "clocks": clocks.summary(),
                 "integrator_only_ns_per_day": 86400.0 / (ms_per_step * 1e-3) * params.step_size * 1e-3,
                 "thermostat": {"ke2": [float(x) for x in st["ke2"]], "vscale": [float(x) for x in st["vscale"]]}}
