@@ -208,6 +208,13 @@ int vvb200_thermostat(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200
 /* accumulate == 0: integrateMiddlePos1 (posDelta = oldDelta = dt/2 v, :154-158); != 0: integrateMiddlePos2 (+=, :169-173) */
 int vvb200_middle_delta(vvb200_plan *plan, const vvb200_buffers *buf, int accumulate, void *stream);
 int vvb200_middle_finish(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);                                  /* integrateMiddlePos3 + applyHardWallConstraints, :179-212 */
+/* The same for the velocity-Verlet scheme (CudaIntegrateVVStepKernel::firstIntegrate / secondIntegrate,
+ * CudaVVKernels.cpp:296-431): velocityVerletIntegrateVelocities (second_half != 0: this step's Langevin force is
+ * computed first, like VVIntegrator.cpp:316-325; update_pos_delta != 0: posDelta = dt v) and
+ * velocityVerletIntegratePositions + applyHardWallConstraints. */
+int vvb200_vv_kick(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, int second_half,
+                   int update_pos_delta, void *stream);
+int vvb200_vv_positions(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);
 int vvb200_update_image_positions(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);                        /* ModifyImageChargeKernel::updateImagePositions, :904-934 */
 
 /* ---- state / observables (each synchronises `stream`) --------------------------------------- */

@@ -143,6 +143,8 @@ def load_library(path=None):
     lib.vvb200_middle_delta.argtypes = [vp, P(_Buffers), C.c_int, vp]
     lib.vvb200_middle_finish.argtypes = [vp, P(_Buffers), vp]
     lib.vvb200_update_image_positions.argtypes = [vp, P(_Buffers), vp]
+    lib.vvb200_vv_kick.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, C.c_int, vp]
+    lib.vvb200_vv_positions.argtypes = [vp, P(_Buffers), vp]
     lib.vvb200_partials_ptr.argtypes = [vp, P(vp), P(i32)]
     lib.vvb200_set_global_thermostat.argtypes = [vp, vp, dbl]
     lib.vvb200_get_thermostat_state.argtypes = [vp, P(_ThermostatState), vp]
@@ -302,6 +304,16 @@ class Plan:
     def middle_finish(self, bufs, stream=None):
         b = bufs.c_struct()
         _check(self.lib, self.lib.vvb200_middle_finish(self.h, C.byref(b), self._stream(stream)))
+
+    def vv_kick(self, bufs, second_half, update_pos_delta, random_index=0, inv_box_z=0.0, stream=None):
+        b = bufs.c_struct()
+        a = _StepArgs(random_index, inv_box_z)
+        _check(self.lib, self.lib.vvb200_vv_kick(self.h, C.byref(b), C.byref(a), int(second_half), int(update_pos_delta),
+                                                 self._stream(stream)))
+
+    def vv_positions(self, bufs, stream=None):
+        b = bufs.c_struct()
+        _check(self.lib, self.lib.vvb200_vv_positions(self.h, C.byref(b), self._stream(stream)))
 
     def update_image_positions(self, bufs, stream=None):
         b = bufs.c_struct()

@@ -386,6 +386,66 @@ __global__ void __launch_bounds__(THREADS) finish_kernel(void *posqRaw, void *co
     }
 }
 
+// posDelta = dt * v after the first half kick (velocityVerlet.cu:24-26)
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) vv_delta_kernel(const void *velmRaw, void *posDeltaRaw, int N, double dt) {
+    typedef typename Prec<MODE>::mixed mixed;
+    typedef typename Prec<MODE>::mixed4 mixed4;
+    const mixed4 *velm = reinterpret_cast<const mixed4 *>(velmRaw);
+    mixed4 *posDelta = reinterpret_cast<mixed4 *>(posDeltaRaw);
+    const mixed stepSize = (mixed) dt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) {
+        const mixed4 v = ld_stream(velm + i);
+        if (v.w != 0) {
+            mixed4 d;
+            d.x = stepSize * v.x; d.y = stepSize * v.y; d.z = stepSize * v.z; d.w = 0;
+            st_stream(posDelta + i, d);
+        }
+    }
+}
+
+// velocityVerletIntegratePositions (velocityVerlet.cu:35-68)
+template <int MODE>
+__global__ void __launch_bounds__(THREADS) vv_positions_kernel(void *posqRaw, void *corrRaw, const void *posDeltaRaw,
+                                                               void *velmRaw, int N, double dt) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    real4 *posq = reinterpret_cast<real4 *>(posqRaw);
+    real4 *corr = reinterpret_cast<real4 *>(corrRaw);
+    mixed4 *velm = reinterpret_cast<mixed4 *>(velmRaw);
+    const mixed4 *posDelta = reinterpret_cast<const mixed4 *>(posDeltaRaw);
+    const mixed invStepSize = (mixed) (1.0 / (mixed) dt);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += blockDim.x * gridDim.x) {
+        mixed4 v = ld_stream(velm + i);
+        if (v.w != 0) {
+            const mixed4 d = ld_stream(posDelta + i);
+            real4 pq = ld_stream(posq + i);
+            v.x = (mixed) (invStepSize * d.x);
+            v.y = (mixed) (invStepSize * d.y);
+            v.z = (mixed) (invStepSize * d.z);
+            if (P::kMixed) {
+                const real4 c = ld_stream(corr + i);
+                mixed x = pq.x + (mixed) c.x, y = pq.y + (mixed) c.y, z = pq.z + (mixed) c.z;
+                x += d.x; y += d.y; z += d.z;
+                real4 oc;
+                splitPos<MODE>(x, pq.x, oc.x);
+                splitPos<MODE>(y, pq.y, oc.y);
+                splitPos<MODE>(z, pq.z, oc.z);
+                oc.w = 0;
+                st_stream(posq + i, pq);
+                st_stream(corr + i, oc);
+            } else {
+                pq.x += d.x; pq.y += d.y; pq.z += d.z;
+                st_stream(posq + i, pq);
+            }
+            st_stream(velm + i, v);
+        }
+    }
+}
+
 // applyHardWallConstraints as a pair gather kernel (middle.cu:106-221), used after OpenMM's position
 // constraints where the fused pass B cannot be.
 template <int MODE>
@@ -1097,6 +1157,71 @@ extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, voi
         break;
     default:
         finish_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, d->oldDelta, b->velm, p->N, p->par.step_size);
+        if (hw) hardwall_pairs_kernel<VVB200_DOUBLE><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
+    }
+    p->launches += hw ? 2 : 1;
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+// velocity-Verlet scheme around OpenMM's constraint kernels (CudaVVKernels.cpp:296-431)
+extern "C" int vvb200_vv_kick(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, int secondHalf,
+                              int updatePosDelta, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_vv_kick", false, true);
+    if (rc) return rc;
+    if (updatePosDelta && !b->pos_delta) {
+        vvb200_set_error("vvb200_vv_kick: pos_delta buffer required");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    if (secondHalf) {
+        // second half: the extra forces of this step (VVIntegrator.cpp:316-325)
+        if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+        p->dev->extraForcesValid = true;
+    }
+    KParams k = makeParams(p, b, a);
+    k.extraForces = p->dev->extraForcesValid ? 1 : 0;
+    k.fuseNHC = 0;
+    CUDA_TRY((dispatchA<KICK_VV>(p->precision, k.cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    if (updatePosDelta) {
+        const int grid = elementwiseGrid(p, p->N);
+        switch (p->precision) {
+        case VVB200_SINGLE: vv_delta_kernel<VVB200_SINGLE><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, p->N, p->par.step_size); break;
+        case VVB200_MIXED: vv_delta_kernel<VVB200_MIXED><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, p->N, p->par.step_size); break;
+        default: vv_delta_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, p->N, p->par.step_size);
+        }
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_vv_positions(vvb200_plan *p, const vvb200_buffers *b, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_vv_positions", true, false);
+    if (rc) return rc;
+    if (!b->pos_delta) {
+        vvb200_set_error("vvb200_vv_positions: pos_delta buffer required");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    vvb200_device_state *d = p->dev;
+    const int grid = elementwiseGrid(p, p->N);
+    const int nPairs = (int) p->drudePairs.size() / 2;
+    const bool hw = p->par.max_drude_distance > 0 && nPairs > 0;
+    const int gridHW = std::max(1, std::min((nPairs + 127) / 128, d->numSM * 8));
+    const double hwScale = std::sqrt(BOLTZ_D * p->par.drude_temperature);
+    switch (p->precision) {
+    case VVB200_SINGLE:
+        vv_positions_kernel<VVB200_SINGLE><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, b->velm, p->N, p->par.step_size);
+        if (hw) hardwall_pairs_kernel<VVB200_SINGLE><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
+        break;
+    case VVB200_MIXED:
+        vv_positions_kernel<VVB200_MIXED><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, b->velm, p->N, p->par.step_size);
+        if (hw) hardwall_pairs_kernel<VVB200_MIXED><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
+        break;
+    default:
+        vv_positions_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(b->posq, b->posq_correction, b->pos_delta, b->velm, p->N, p->par.step_size);
         if (hw) hardwall_pairs_kernel<VVB200_DOUBLE><<<gridHW, 128, 0, st>>>(b->posq, b->posq_correction, b->velm, d->drudePairs, nPairs, p->par.step_size, p->par.max_drude_distance, hwScale);
     }
     p->launches += hw ? 2 : 1;

@@ -259,3 +259,30 @@ def test_large_system_properties(vv, vo):
     oracle.scale_velocity(want)
     got = bufs.to_host()
     assert rel_err(got.velm[: spec.n, :3], want.velm[: spec.n, :3]) <= 1e-6
+
+
+def test_vv_split_entry_points_match_fused(vv, vo):
+    """velocity-Verlet scheme through the VVKernels.h-shaped calls (thermostat / half kick + posDelta / positions /
+    half kick / thermostat, as the OpenMM glue issues them around constraints) == the fused vv_first + vv_second"""
+    import torch
+    spec = vv.make_edl(n_ion_pairs=32, n_electrode=300, electrode_molecules=3)
+    params = dataclasses.replace(vv.Params(max_drude_distance=0.02, mirror_location=1.5,
+                                           electric_field=0.25 * 1.60217662e-22).resolved_for(spec),
+                                 use_middle_scheme=False)
+    host = vv.make_state(spec, "mixed", n_random=4 * 302, mirror=1.5)
+    pa, pb = vv.Plan(spec, params, "mixed").upload(), vv.Plan(spec, params, "mixed").upload()
+    a, b = vv.DeviceBuffers(host), vv.DeviceBuffers(host, with_pos_delta=True)
+    ri = 0
+    for _ in range(3):
+        pa.step_vv_first(a, random_index=ri)
+        pa.step_vv_second(a, random_index=ri)
+        pb.thermostat(b)
+        pb.vv_kick(b, second_half=False, update_pos_delta=True, random_index=ri)
+        pb.vv_positions(b)
+        pb.update_image_positions(b)
+        pb.vv_kick(b, second_half=True, update_pos_delta=False, random_index=ri)
+        pb.thermostat(b)
+        ri += pa.random_request
+    torch.cuda.synchronize()
+    ha, hb = a.to_host(), b.to_host()
+    assert np.array_equal(hb.velm, ha.velm) and np.array_equal(hb.posq, ha.posq) and np.array_equal(hb.corr, ha.corr)
