@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     const mixed Vb = cosine ? (mixed) p.nhc->vBias : (mixed) 0;
     const mixed maxD = (mixed) p.maxDrudeDistance;
     // conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold
-    const mixed maxD2safe = maxD * maxD * (mixed) (1.0 - 1e-4);
+    const real maxD2safe = (real) (p.maxDrudeDistance * p.maxDrudeDistance * (1.0 - 1e-4));
     const mixed hwScale = (mixed) p.hardwallScale;
     const real efscale = (real) p.efscale;
     const real accel = (real) p.accel;
@@ -602,14 +602,16 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
             real4 pq;
             pq.x = pq.y = pq.z = pq.w = 0;
             mixed xs[3] = {0, 0, 0};
+            real4 cs;
+            cs.x = cs.y = cs.z = cs.w = 0;
             if (Stage::POSQ) {
                 pq = st.posq[sl];
                 xs[0] = pq.x; xs[1] = pq.y; xs[2] = pq.z;
                 if (Stage::CORR) {
-                    const real4 c = st.corr[sl];
-                    xs[0] = pq.x + (mixed) c.x;       // middle.cu:82-84
-                    xs[1] = pq.y + (mixed) c.y;
-                    xs[2] = pq.z + (mixed) c.z;
+                    cs = st.corr[sl];
+                    xs[0] = pq.x + (mixed) cs.x;       // middle.cu:82-84
+                    xs[1] = pq.y + (mixed) cs.y;
+                    xs[2] = pq.z + (mixed) cs.z;
                 }
             }
             double cphs = 0, cq = 0;
@@ -631,19 +633,18 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
             mixed vs[3] = {vel.x, vel.y, vel.z};
             const mixed ws = vel.w;
             mixed vq[3] = {0, 0, 0}, wq = 0;
-            mixed xq[3] = {0, 0, 0};
-            real4 pqq;
+            // the partner's position stays in its raw (posq, posqCorrection) form: it is only converted when the
+            // hard wall's pre-test cannot rule the wall out
+            real4 pqq, cqr;
             pqq.x = pqq.y = pqq.z = pqq.w = 0;
+            cqr.x = cqr.y = cqr.z = cqr.w = 0;
+            mixed ds[3] = {0, 0, 0}, dq[3] = {0, 0, 0};      // position increments of this particle / its partner
             if (role != VVB200_ROLE_NONE) {
                 const mixed4 v2 = st.velm[psl];
                 vq[0] = v2.x; vq[1] = v2.y; vq[2] = v2.z; wq = v2.w;
                 if (Stage::POSQ) {
                     pqq = st.posq[psl];
-                    xq[0] = pqq.x; xq[1] = pqq.y; xq[2] = pqq.z;
-                    if (Stage::CORR) {
-                        const real4 c = st.corr[psl];
-                        xq[0] = pqq.x + (mixed) c.x; xq[1] = pqq.y + (mixed) c.y; xq[2] = pqq.z + (mixed) c.z;
-                    }
+                    if (Stage::CORR) cqr = st.corr[psl];
                     if (cosine) cq = cosPhase((double) pqq.z, (double) invBoxZ);
                 }
             }
@@ -737,18 +738,17 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
                 if (ws != 0) {
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
-                        const mixed delta = stepSize * vs[d];
-                        xs[d] += delta;
-                        vs[d] = (mixed) (invStepSize * delta);
+                        ds[d] = stepSize * vs[d];
+                        xs[d] += ds[d];
+                        vs[d] = (mixed) (invStepSize * ds[d]);
                     }
                     writePos = writeVel = true;
                 }
                 if (role != VVB200_ROLE_NONE && wq != 0) {
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
-                        const mixed delta = stepSize * vq[d];
-                        xq[d] += delta;
-                        vq[d] = (mixed) (invStepSize * delta);
+                        dq[d] = stepSize * vq[d];
+                        vq[d] = (mixed) (invStepSize * dq[d]);
                     }
                 }
             } else {
@@ -757,38 +757,47 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
                 if (ws != 0) {
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
-                        mixed delta = halfdt * vs0[d];
-                        delta += halfdt * vs[d];
-                        xs[d] += delta;
+                        ds[d] = halfdt * vs0[d];
+                        ds[d] += halfdt * vs[d];
+                        xs[d] += ds[d];
                     }
                     writePos = writeVel = true;
                 }
                 if (role != VVB200_ROLE_NONE && wq != 0) {
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
-                        mixed delta = halfdt * vq0[d];
-                        delta += halfdt * vq[d];
-                        xq[d] += delta;
+                        dq[d] = halfdt * vq0[d];
+                        dq[d] += halfdt * vq[d];
                     }
                 }
             }
 
             // ---- Drude hard wall (middle.cu:114-220), evaluated by both members of the pair ----------
             if (p.hardwall && role != VVB200_ROLE_NONE) {
-                // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
-                if (P::kMixed) {
+                // Pre-test in `real` arithmetic on the raw operands: the new separation is (posq_s - posq_q) +
+                // (corr_s - corr_q) + (ds - dq); the first difference is exact or off by < 4e-9 nm (neighbouring floats),
+                // so the squared distance is good to ~1e-6 relative and a 1e-4 margin is conservative.  Only a pair
+                // that might touch the wall pays for the partner's fp64 position and the reference's sqrt / reciprocal.
+                const real sx = (pq.x - pqq.x) + (cs.x - cqr.x) + (real) (ds[0] - dq[0]);
+                const real sy = (pq.y - pqq.y) + (cs.y - cqr.y) + (real) (ds[1] - dq[1]);
+                const real sz = (pq.z - pqq.z) + (cs.z - cqr.z) + (real) (ds[2] - dq[2]);
+                if (!(sx * sx + sy * sy + sz * sz < maxD2safe)) {
+                    mixed xq[3] = {pqq.x + (mixed) cqr.x, pqq.y + (mixed) cqr.y, pqq.z + (mixed) cqr.z};
 #pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        real hi, lo;
-                        if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
-                        if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
+                    for (int d = 0; d < 3; d++) xq[d] += dq[d];
+                    // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
+                    if (P::kMixed) {
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            real hi, lo;
+                            if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
+                            if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
+                        }
                     }
-                }
-                const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
-                mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
-                const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
-                const mixed d2 = dx * dx + dy * dy + dz * dz;
-                if (!(d2 < maxD2safe)) {
+                    const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
+                    mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
+                    const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
+                    const mixed d2 = dx * dx + dy * dy + dz * dz;
                     mixed *vel1 = selfIsDrude ? vs : vq, *vel2 = selfIsDrude ? vq : vs;
                     const mixed w1 = selfIsDrude ? ws : wq, w2 = selfIsDrude ? wq : ws;
                     const mixed r = vv_sqrt<MODE, mixed>(d2);
