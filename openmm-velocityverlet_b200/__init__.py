@@ -24,6 +24,7 @@ from .system import (  # noqa: F401
     make_bulk_ionic_liquid,
     make_edl,
     make_nonpolar_box,
+    make_polymer,
     make_ragged,
     make_state,
     np_dtypes,

@@ -129,7 +129,7 @@ struct KParams {
     unsigned int *counter;
     double dt;
     double efscale, accel, invBoxZ, maxDrudeDistance, hardwallScale;
-    int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC, cosine;
+    int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC, cosine, kickOnly;
     int stagesA, stagesB;
 };
 
@@ -211,6 +211,7 @@ __global__ void nhc_kernel(NhcDevice *s, double dt) {
 }
 
 #include "vvb200_stream.cuh"
+#include "vvb200_general.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // small gather kernels
@@ -554,6 +555,10 @@ struct vvb200_device_state {
     uint32_t *slotMeta = nullptr;
     int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
     int2 *pairsLD = nullptr, *imagePairs = nullptr, *drudePairs = nullptr;
+    // any-topology path
+    int32_t *moleculesNH = nullptr, *normalNH = nullptr, *particleMolId = nullptr;
+    int2 *pairsNH = nullptr;
+    void *ownPosDelta = nullptr;
     void *oldDelta = nullptr;   // mixed4[N], plugin-owned like the reference's (CudaVVKernels.cpp:90-96)
     void *comV = nullptr, *comCbar = nullptr, *ldForce = nullptr;
     double *partials = nullptr;
@@ -643,11 +648,6 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     p->dev = d;
     CUDA_TRY(cudaGetDevice(&d->device));
     CUDA_TRY(cudaDeviceGetAttribute(&d->numSM, cudaDevAttrMultiProcessorCount, d->device));
-    if (!p->tiled) {
-        vvb200_set_error("vvb200_plan_upload: topology not supported by the tiled kernels (%s)", p->tiledWhyNot.c_str());
-        vvb200_device_free(p);
-        return VVB200_ERR_UNSUPPORTED_TOPOLOGY;
-    }
     d->numTiles = (int) p->tileStart.size() - 1;
 
     // per tile-local molecule: first slot, count, contiguity
@@ -699,6 +699,12 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     if ((rc = uploadVec(d, &d->pairsLD, p->pairsLD.data(), p->pairsLD.size() / 2, st))) return rc;
     if ((rc = uploadVec(d, &d->imagePairs, p->imagePairs.data(), p->imagePairs.size() / 2, st))) return rc;
     if ((rc = uploadVec(d, &d->drudePairs, p->drudePairs.data(), p->drudePairs.size() / 2, st))) return rc;
+    if (!p->tiled) {
+        if ((rc = uploadVec(d, &d->moleculesNH, p->moleculesNH.data(), p->moleculesNH.size(), st))) return rc;
+        if ((rc = uploadVec(d, &d->normalNH, p->normalNH.data(), p->normalNH.size(), st))) return rc;
+        if ((rc = uploadVec(d, &d->pairsNH, p->pairsNH.data(), p->pairsNH.size() / 2, st))) return rc;
+        if ((rc = uploadVec(d, &d->particleMolId, p->particleMolId.data(), p->particleMolId.size(), st))) return rc;
+    }
 
     const size_t ms = mixedSize(p->precision), rs = realSize(p->precision);
     unsigned char *raw = nullptr;
@@ -793,6 +799,7 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.extraForces = 1;
     k.fuseNHC = 1;
     k.cosine = p->par.cos_acceleration != 0;
+    k.kickOnly = p->tiled ? 0 : 1;
     return k;
 }
 
@@ -980,11 +987,106 @@ extern "C" int vvb200_profile_read(vvb200_plan *p, double *msPassA, double *msPa
     return VVB200_OK;
 }
 
+
+// ---- any-topology path (vvb200_general.cuh) --------------------------------------------------------------------
+static GParams makeGParams(const vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a) {
+    const vvb200_device_state *d = p->dev;
+    GParams g;
+    memset(&g, 0, sizeof g);
+    g.N = p->N;
+    g.nMolNH = (int) p->moleculesNH.size();
+    g.nNormal = (int) p->normalNH.size();
+    g.nPairs = (int) p->pairsNH.size() / 2;
+    g.moleculesNH = d->moleculesNH; g.normalNH = d->normalNH; g.particleMolId = d->particleMolId;
+    g.sortedByMol = d->sortedByMol; g.particlesInMolecules = d->particlesInMolecules; g.pairsNH = d->pairsNH;
+    g.velm = b->velm; g.posq = b->posq; g.comV = d->comV; g.comCbar = d->comCbar;
+    g.partials = d->partials; g.nhc = d->nhc; g.counter = d->counter;
+    g.dt = p->par.step_size;
+    g.invBoxZ = a ? a->inv_box_z : 0.0;
+    g.useCOM = p->par.use_com_temp_group != 0 && !p->moleculesNH.empty();
+    g.cosine = p->par.cos_acceleration != 0;
+    g.fuseNHC = 1;
+    return g;
+}
+
+template <int MODE>
+static void launchGeneralThermostat(const GParams &g, int numSM, bool reduce, bool scale, cudaStream_t st) {
+    const int work = std::max(std::max(g.nNormal, g.nPairs), std::max(g.nMolNH, g.cosine ? g.N : 0));
+    const int grid = std::max(1, std::min((work + 255) / 256, numSM * 8));
+    if (reduce) {
+        if (g.useCOM) {
+            const int gridCom = std::max(1, std::min((g.nMolNH + 7) / 8, numSM * 8));
+            general_com_kernel<MODE><<<gridCom, 256, 0, st>>>(g);
+        }
+        general_ke_kernel<MODE><<<grid, 256, 0, st>>>(g);
+    }
+    if (scale)
+        general_scale_kernel<MODE><<<grid, 256, 0, st>>>(g);
+}
+
+// reduce: COM velocities + group energies (+ NH chains when fuse); scale: in-place velocity scaling
+static int generalThermostat(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, bool reduce, bool fuse,
+                             bool scale, cudaStream_t st) {
+    if (p->par.cos_acceleration != 0 && !b->posq) {
+        vvb200_set_error("vvb200: posq required for the cosine perturbation");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    GParams g = makeGParams(p, b, a);
+    g.fuseNHC = fuse ? 1 : 0;
+    switch (p->precision) {
+    case VVB200_SINGLE: launchGeneralThermostat<VVB200_SINGLE>(g, p->dev->numSM, reduce, scale, st); break;
+    case VVB200_MIXED: launchGeneralThermostat<VVB200_MIXED>(g, p->dev->numSM, reduce, scale, st); break;
+    default: launchGeneralThermostat<VVB200_DOUBLE>(g, p->dev->numSM, reduce, scale, st);
+    }
+    p->launches += (reduce ? (g.useCOM ? 2 : 1) : 0) + (scale ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return VVB200_OK;
+}
+
+// the general path needs posDelta; standalone callers may not own one
+static int withPosDelta(vvb200_plan *p, const vvb200_buffers *b, vvb200_buffers *out, cudaStream_t st) {
+    *out = *b;
+    if (out->pos_delta)
+        return VVB200_OK;
+    vvb200_device_state *d = p->dev;
+    if (!d->ownPosDelta) {
+        const size_t bytes = (size_t) p->paddedN * 4 * (p->precision == VVB200_SINGLE ? 4 : 8);
+        CUDA_TRY(cudaMalloc(&d->ownPosDelta, bytes));
+        d->allocations.push_back(d->ownPosDelta);
+        CUDA_TRY(cudaMemsetAsync(d->ownPosDelta, 0, bytes, st));
+    }
+    out->pos_delta = d->ownPosDelta;
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_middle_delta(vvb200_plan *p, const vvb200_buffers *b, int accumulate, void *stream);
+extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, void *stream);
+extern "C" int vvb200_vv_positions(vvb200_plan *p, const vvb200_buffers *b, void *stream);
+template <int MODE> __global__ void vv_delta_kernel(const void *, void *, int, double);
+
+static int generalKick(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, int kick, bool extraForces,
+                       cudaStream_t st) {
+    KParams k = makeParams(p, b, a);
+    k.fuseNHC = 0;
+    k.extraForces = extraForces ? 1 : 0;
+    if (kick == KICK_MIDDLE) CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, k.cosine, k, p->dev->numSM, st)));
+    else CUDA_TRY((dispatchA<KICK_VV>(p->precision, k.cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    return VVB200_OK;
+}
+
 extern "C" int vvb200_middle_kick_reduce(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
     int rc = checkStepArgs(p, b, "vvb200_middle_kick_reduce", false, true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t) stream;
     if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+    if (!p->tiled) {
+        vvb200_buffers bb;
+        if ((rc = withPosDelta(p, b, &bb, st))) return rc;
+        if ((rc = generalKick(p, &bb, a, KICK_MIDDLE, true, st))) return rc;
+        if ((rc = vvb200_middle_delta(p, &bb, 0, stream))) return rc;
+        return hasNH(p) ? generalThermostat(p, &bb, a, true, false, false, st) : VVB200_OK;
+    }
     KParams k = makeParams(p, b, a);
     k.fuseNHC = 0;
     profMark(p->dev, 0, st);
@@ -1009,6 +1111,14 @@ extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffer
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t) stream;
     if (hasNH(p) && (rc = launchNhc(p, st))) return rc;
+    if (!p->tiled) {
+        vvb200_buffers bb;
+        if ((rc = withPosDelta(p, b, &bb, st))) return rc;
+        if (hasNH(p) && (rc = generalThermostat(p, &bb, a, false, false, true, st))) return rc;
+        if ((rc = vvb200_middle_delta(p, &bb, 1, stream))) return rc;
+        if ((rc = vvb200_middle_finish(p, &bb, stream))) return rc;
+        return vvb200_update_image_positions(p, b, stream);
+    }
     KParams k = makeParams(p, b, a);
     // the pass-B interval of the split path starts here (the all-reduce and the NHC block are not in it)
     profMark(p->dev, 2, st);
@@ -1034,6 +1144,18 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
     cudaStream_t st = (cudaStream_t) stream;
     const bool cosine = p->par.cos_acceleration != 0;
     if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+    if (!p->tiled) {
+        // any topology: kick | posDelta = dt/2 v | thermostat (gather kernels, NH chains on the device) |
+        // posDelta += dt/2 v' | position write + hard wall | images
+        vvb200_buffers bb;
+        if ((rc = withPosDelta(p, b, &bb, st))) return rc;
+        if ((rc = generalKick(p, &bb, a, KICK_MIDDLE, true, st))) return rc;
+        if ((rc = vvb200_middle_delta(p, &bb, 0, stream))) return rc;
+        if (hasNH(p) && (rc = generalThermostat(p, &bb, a, true, true, true, st))) return rc;
+        if ((rc = vvb200_middle_delta(p, &bb, 1, stream))) return rc;
+        if ((rc = vvb200_middle_finish(p, &bb, stream))) return rc;
+        return vvb200_update_image_positions(p, b, stream);
+    }
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
     profMark(p->dev, 0, st);
@@ -1052,6 +1174,21 @@ extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, con
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t) stream;
     const bool cosine = p->par.cos_acceleration != 0;
+    if (!p->tiled) {
+        vvb200_buffers bb;
+        if ((rc = withPosDelta(p, b, &bb, st))) return rc;
+        if (hasNH(p) && (rc = generalThermostat(p, &bb, a, true, true, true, st))) return rc;
+        if ((rc = generalKick(p, &bb, a, KICK_VV, p->dev->extraForcesValid, st))) return rc;
+        const int grid = std::max(1, std::min((p->N + THREADS - 1) / THREADS, p->dev->numSM * 8));
+        switch (p->precision) {
+        case VVB200_SINGLE: vv_delta_kernel<VVB200_SINGLE><<<grid, THREADS, 0, st>>>(bb.velm, bb.pos_delta, p->N, p->par.step_size); break;
+        case VVB200_MIXED: vv_delta_kernel<VVB200_MIXED><<<grid, THREADS, 0, st>>>(bb.velm, bb.pos_delta, p->N, p->par.step_size); break;
+        default: vv_delta_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(bb.velm, bb.pos_delta, p->N, p->par.step_size);
+        }
+        p->launches++;
+        if ((rc = vvb200_vv_positions(p, &bb, stream))) return rc;
+        return vvb200_update_image_positions(p, b, stream);
+    }
     KParams k = makeParams(p, b, a);
     k.extraForces = p->dev->extraForcesValid ? 1 : 0;
     if (hasNH(p)) {
@@ -1070,6 +1207,10 @@ extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, co
     const bool cosine = p->par.cos_acceleration != 0;
     if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
     p->dev->extraForcesValid = true;
+    if (!p->tiled) {
+        if ((rc = generalKick(p, b, a, KICK_VV, true, st))) return rc;
+        return hasNH(p) ? generalThermostat(p, b, a, true, true, true, st) : VVB200_OK;
+    }
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
     CUDA_TRY((dispatchA<KICK_VV>(p->precision, cosine, k, p->dev->numSM, st)));
@@ -1085,6 +1226,13 @@ extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, co
 extern "C" int vvb200_middle_kick(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
     // extra forces + integrateMiddleVel; the reductions that ride along are discarded because OpenMM's
     // applyVelocityConstraints runs next (CudaVVKernels.cpp:144-151)
+    if (p && p->dev && !p->tiled) {
+        int rc = checkStepArgs(p, b, "vvb200_middle_kick", false, true);
+        if (rc) return rc;
+        cudaStream_t st = (cudaStream_t) stream;
+        if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+        return generalKick(p, b, a, KICK_MIDDLE, true, st);
+    }
     return vvb200_middle_kick_reduce(p, b, a, stream);
 }
 
@@ -1095,6 +1243,8 @@ extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const 
         return VVB200_OK;
     cudaStream_t st = (cudaStream_t) stream;
     const bool cosine = p->par.cos_acceleration != 0;
+    if (!p->tiled)
+        return generalThermostat(p, b, a, true, true, true, st);
     KParams k = makeParams(p, b, a);
     CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -114,6 +115,7 @@ static int conflict(vvb200_plan *p, const char *msg) {
 }
 
 static bool buildTiles(vvb200_plan *p);
+static bool buildPlainTiles(vvb200_plan *p);
 
 extern "C" int vvb200_plan_create(const vvb200_system *sys, const vvb200_params *par, int precision,
                                   vvb200_plan **out) {
@@ -311,6 +313,15 @@ extern "C" int vvb200_plan_create(const vvb200_system *sys, const vvb200_params 
     p->totalMassGlobal = massTotal;
 
     p->tiled = buildTiles(p);
+    if (p->tiled && getenv("VVB200_FORCE_GENERAL")) {     // testing hook: exercise the any-topology path
+        p->tiled = false;
+        p->tiledWhyNot = "forced by VVB200_FORCE_GENERAL";
+    }
+    if (!p->tiled && !buildPlainTiles(p)) {
+        vvb200_set_error("vvb200_plan_create: %s", p->tiledWhyNot.c_str());
+        delete p;
+        return VVB200_ERR_UNSUPPORTED_TOPOLOGY;
+    }
     *out = p;
     return VVB200_OK;
 }
@@ -439,6 +450,45 @@ static bool buildTiles(vvb200_plan *p) {
 
     // compact Langevin-force slots: normal i -> i, pair k -> nNormal + 2k (Drude), +1 (parent):
     // the same positions as the reference's random-number indices (drudeLangevin.cu:20,45-46)
+    if (!p->particlesLD.empty()) {
+        p->ldSlot.assign(N, -1);
+        for (size_t i = 0; i < p->normalLD.size(); i++)
+            p->ldSlot[p->normalLD[i]] = (int32_t) i;
+        const int32_t base = (int32_t) p->normalLD.size();
+        for (size_t k = 0; k < p->pairsLD.size(); k += 2) {
+            p->ldSlot[p->pairsLD[k]] = base + (int32_t) k;
+            p->ldSlot[p->pairsLD[k + 1]] = base + (int32_t) k + 1;
+        }
+    }
+    return true;
+}
+
+// Tables of the any-topology path: fixed 512-slot tiles that only the element-wise kick uses (pass A with its
+// molecule and pair phases switched off); the thermostat runs through gather kernels over the reference's own index
+// arrays (normalNH, pairsNH, sortedByMol, ...), so nothing has to be tile-local.
+static bool buildPlainTiles(vvb200_plan *p) {
+    const int N = p->N;
+    std::vector<int32_t> elecCount(N, 0);
+    for (int32_t i : p->particlesElectrolyte)
+        if (++elecCount[i] > (int) VVB200_META_ELEC_MASK) {
+            p->tiledWhyNot = "a particle appears more than 7 times in the electrolyte list";
+            return false;
+        }
+    p->tileStart.clear();
+    for (int32_t s = 0; s < N; s += VVB200_TILE_CAP)
+        p->tileStart.push_back(s);
+    p->tileStart.push_back(N);
+    const int numTiles = (int) p->tileStart.size() - 1;
+    p->tileMolOffset.assign(numTiles + 1, 0);
+    p->tileMolList.clear();
+    p->slotMeta.assign(N, 0);
+    for (int i = 0; i < N; i++) {
+        uint32_t word = VVB200_META_MOL_NONE | ((uint32_t) elecCount[i] << VVB200_META_ELEC_SHIFT);
+        if (p->isNH[i]) word |= VVB200_META_NH;
+        if (p->isLD[i]) word |= VVB200_META_LD;
+        word |= (uint32_t) VVB200_META_PARTNER_BIAS << VVB200_META_PARTNER_SHIFT;
+        p->slotMeta[i] = word;
+    }
     if (!p->particlesLD.empty()) {
         p->ldSlot.assign(N, -1);
         for (size_t i = 0; i < p->normalLD.size(); i++)

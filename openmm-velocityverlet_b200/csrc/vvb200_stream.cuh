@@ -266,6 +266,10 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
         if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
         mbarArrive(empty + s);      // this thread no longer needs the stage: the producer may refill it
         if (++s == stages) { s = 0; phase ^= 1; }
+        if (p.kickOnly) {           // any-topology path: the thermostat runs in the gather kernels
+            buf ^= 1;
+            continue;
+        }
         consumerBarrier();
 
         // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30): COM_LANES lanes per

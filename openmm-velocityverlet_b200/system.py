@@ -190,6 +190,31 @@ def make_nonpolar_box(n_molecules=512, atoms_per_molecule=8, has_cmm=True):
     return spec.finalize(mol_id=mol_id)
 
 
+def make_polymer(n_chains=3, chain_len=700, n_solvent=40, has_cmm=False):
+    """Polarizable polymer chains under NH: each chain is ONE molecule of 2*chain_len particles (backbone atom +
+    its Drude, parents listed first then all Drudes, so partners sit chain_len slots apart) -- neither the molecule nor
+    the pairs fit a 512-slot tile.  Plus a few small solvent molecules.  Exercises the any-topology path."""
+    masses, bonds, pairs = [], [], []
+    base = 0
+    for _ in range(n_chains):
+        for k in range(chain_len):
+            masses.append(13.607 if k % 2 == 0 else 11.611)
+            if k:
+                bonds.append((base + k - 1, base + k))
+        for k in range(chain_len):
+            masses.append(0.4)
+            pairs.append((base + chain_len + k, base + k))
+            bonds.append((base + k, base + chain_len + k))
+        base += 2 * chain_len
+    for _ in range(n_solvent):
+        masses.extend([15.999, 1.008, 1.008])
+        bonds.extend([(base, base + 1), (base, base + 2)])
+        base += 3
+    spec = SystemSpec(n=base, masses=np.array(masses), bonds=np.array(bonds, np.int32), drude_pairs=np.array(pairs, np.int32),
+                      has_cmm=has_cmm, name=f"polymer_{n_chains}x{chain_len}")
+    return spec.finalize()
+
+
 def make_edl(n_ion_pairs=511, n_electrode=2496, electrode_molecules=4, name=None):
     """BASELINE config 3 (examples/run-edl.py): Langevin electrode atoms, NH + external field on the
     electrolyte, one massless image particle per electrolyte particle bonded into its parent's
