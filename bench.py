@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
+                    help="multi-GPU exchange of the 10-double reduction vector: NVLink peer memory inside the NHC kernel, or NCCL")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     return ap.parse_args()
 
@@ -242,7 +244,7 @@ def main():
     host = vv.make_state(spec, args.precision, seed=12345 + 100 * rank, force_sigma=FORCE_SIGMA)
     # this rank holds one whole-molecule partition of a box `world` times larger: DistributedPlan all-reduces the
     # thermostat DOFs and the total mass of the whole box at set-up (world == 1: the plan's own)
-    dplan = vv.DistributedPlan(spec, params, args.precision).upload()
+    dplan = vv.DistributedPlan(spec, params, args.precision).upload(peer={"auto": None, "nccl": False, "peer": True}[args.exchange])
     plan = dplan.plan
     bufs = vv.DeviceBuffers(host)
     n_local = spec.n
@@ -275,7 +277,7 @@ def main():
         e1.record(stream)
         barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = plan.launch_count - launches0 + (K if world > 1 else 0)   # + NCCL's all-reduce kernel
+    launches = plan.launch_count - launches0 + (K if world > 1 and not dplan.peer else 0)   # + NCCL's all-reduce kernel
     ms_a, ms_b, prof_steps = plan.profile_read()
     plan.profile_enable(0)
     if world > 1:
@@ -394,7 +396,9 @@ def main():
                 "config": {"workload": workload_name(args, world), "precision": args.precision,
                            "particles_per_gpu": n_local, "particles_total": n_global,
                            "l2": "inputs larger than L2 (1.4 GB of state per GPU vs 126 MB)",
-                           "parallelism": f"molecule-partitioned x{world}" if world > 1 else "single GPU"},
+                           "parallelism": f"molecule-partitioned x{world}" if world > 1 else "single GPU",
+                           "exchange": ("NVLink peer memory, fused into the NH-chain kernel" if dplan.peer else
+                                        "NCCL all-reduce of 10 doubles") if world > 1 else "none"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "reference_kernels_on_gpu": ref_gpu,
                 "clocks": clocks.summary(),

@@ -191,6 +191,13 @@ int vvb200_step_vv_second(vvb200_plan *plan, const vvb200_buffers *buf, const vv
  *   nhc_scale_drift : NH chains from the reduced sums (redundantly on every rank) + pass B. */
 int vvb200_middle_kick_reduce(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);
 int vvb200_middle_nhc_scale_drift(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);
+/* Alternative to the caller's all-reduce, for one-process-per-GPU runs on an NVLink box: the ranks exchange the
+ * reduction vector through cudaIpc-mapped peer memory INSIDE the single-block kernel that advances the NH chains
+ * (vvb200_middle_nhc_scale_drift then needs no collective in front of it).  Every rank calls vvb200_peer_export
+ * (64-byte cudaIpcMemHandle_t out), the handles are gathered by any means (rank-major, 64 bytes each), every rank
+ * calls vvb200_peer_attach.  world <= 8.  All ranks must then step in lockstep (same number of calls). */
+int vvb200_peer_export(vvb200_plan *plan, void *handle_out_64_bytes);
+int vvb200_peer_attach(vvb200_plan *plan, int rank, int world, const void *handles_rank_major);
 /* device pointer to the fp64 reduction vector and its length (<= 16 doubles) */
 int vvb200_partials_ptr(vvb200_plan *plan, void **device_ptr, int32_t *num_doubles);
 /* Thermostat degrees of freedom / NkbT / eta masses / total mass of the WHOLE system when this

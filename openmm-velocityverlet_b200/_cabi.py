@@ -146,6 +146,8 @@ def load_library(path=None):
     lib.vvb200_vv_kick.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, C.c_int, vp]
     lib.vvb200_vv_positions.argtypes = [vp, P(_Buffers), vp]
     lib.vvb200_partials_ptr.argtypes = [vp, P(vp), P(i32)]
+    lib.vvb200_peer_export.argtypes = [vp, vp]
+    lib.vvb200_peer_attach.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.vvb200_set_global_thermostat.argtypes = [vp, vp, dbl]
     lib.vvb200_get_thermostat_state.argtypes = [vp, P(_ThermostatState), vp]
     lib.vvb200_set_thermostat_state.argtypes = [vp, P(_ThermostatState), vp]
@@ -338,6 +340,16 @@ class Plan:
         p, n = C.c_void_p(), C.c_int32()
         _check(self.lib, self.lib.vvb200_partials_ptr(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def peer_export(self):
+        """64-byte cudaIpcMemHandle_t of this rank's exchange buffer"""
+        h = np.zeros(64, dtype=np.uint8)
+        _check(self.lib, self.lib.vvb200_peer_export(self.h, _ptr(h)))
+        return h
+
+    def peer_attach(self, rank, world, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(world, 64)
+        _check(self.lib, self.lib.vvb200_peer_attach(self.h, int(rank), int(world), _ptr(handles)))
 
     def set_global_thermostat(self, dof3, total_mass):
         dof3 = np.ascontiguousarray(dof3, dtype=np.float64)

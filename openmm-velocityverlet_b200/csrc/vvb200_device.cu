@@ -210,6 +210,69 @@ __global__ void nhc_kernel(NhcDevice *s, double dt) {
         nhcFinish<COS>(s, dt, threadIdx.x);
 }
 
+// ---- all-reduce of the reduction vector over NVLink peer memory, fused with the NH-chain update ----------------
+// Multi-GPU runs (one process per GPU, particles partitioned by whole molecules) need ONE exchange per step: the sum
+// over ranks of <= 10 doubles.  Instead of a separate NCCL launch, the single-block kernel that advances the chains
+// does it itself: every rank stores its vector into a slot of every peer's exchange buffer (cudaIpc-mapped, plain
+// st.global over NVLink), publishes a sequence number with release semantics, waits for the other ranks' numbers
+// with acquire loads, sums the slots in rank order (=> bitwise identical on every rank) and goes on to the chains.
+// Slots are double-buffered by step parity; a rank cannot run two steps ahead because it needs every peer's flag of
+// the step in between.  The wait is bounded (~2 s): on expiry the sums become NaN instead of hanging the GPU.
+#define VVB200_MAX_RANKS 8
+struct PeerSlots {
+    double data[2][VVB200_MAX_RANKS][16];
+    unsigned long long flag[2][VVB200_MAX_RANKS];
+};
+struct PeerCtx {
+    PeerSlots *buf[VVB200_MAX_RANKS];    // buf[r] = rank r's exchange buffer as mapped in this process
+    int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool COS>
+__global__ void nhc_peer_kernel(NhcDevice *s, const PeerCtx ctx, unsigned long long seq, double dt) {
+    __shared__ int expired;
+    const int t = threadIdx.x, par = (int) (seq & 1);
+    if (t == 0) expired = 0;
+    __syncthreads();
+    if (t < ctx.world) {
+        // my vector into rank t's buffer, slot [parity][my rank]
+        double *dst = ctx.buf[t]->data[par][ctx.rank];
+        for (int k = 0; k < VVB200_NRED; k++)
+            dst[k] = s->red[k];
+        __threadfence_system();
+        st_release_sys(&ctx.buf[t]->flag[par][ctx.rank], seq);
+        // wait for rank t's vector in MY buffer
+        const unsigned long long *f = &ctx.buf[ctx.rank]->flag[par][t];
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != seq) {
+            if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: a peer died; do not hang the device
+                expired = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (t < VVB200_NRED) {
+        double v = 0;
+        for (int r = 0; r < ctx.world; r++)
+            v += ctx.buf[ctx.rank]->data[par][r][t];
+        s->red[t] = expired ? __longlong_as_double(0x7ff8000000000000LL) : v;
+    }
+    __syncthreads();
+    if (t < 3)
+        nhcFinish<COS>(s, dt, t);
+}
+
 #include "vvb200_stream.cuh"
 #include "vvb200_general.cuh"
 
@@ -559,6 +622,12 @@ struct vvb200_device_state {
     int32_t *moleculesNH = nullptr, *normalNH = nullptr, *particleMolId = nullptr;
     int2 *pairsNH = nullptr;
     void *ownPosDelta = nullptr;
+    // NVLink peer exchange (multi-GPU)
+    PeerSlots *peerLocal = nullptr;
+    PeerCtx peer{};
+    bool peerAttached = false;
+    unsigned long long peerSeq = 0;
+    std::vector<void *> peerMapped;
     void *oldDelta = nullptr;   // mixed4[N], plugin-owned like the reference's (CudaVVKernels.cpp:90-96)
     void *comV = nullptr, *comCbar = nullptr, *ldForce = nullptr;
     double *partials = nullptr;
@@ -609,6 +678,8 @@ void vvb200_device_free(vvb200_plan *plan) {
         cudaFree(ptr);
     for (cudaEvent_t e : d->profEvents)
         cudaEventDestroy(e);
+    for (void *m : d->peerMapped)
+        cudaIpcCloseMemHandle(m);
     delete d;
     plan->dev = nullptr;
 }
@@ -1097,6 +1168,18 @@ extern "C" int vvb200_middle_kick_reduce(vvb200_plan *p, const vvb200_buffers *b
 }
 
 static int launchNhc(vvb200_plan *p, cudaStream_t st) {
+    vvb200_device_state *d = p->dev;
+    if (d->peerAttached) {
+        // all-reduce over peer memory + NH chains in one single-block kernel (no NCCL launch)
+        const unsigned long long seq = ++d->peerSeq;
+        if (p->par.cos_acceleration != 0)
+            nhc_peer_kernel<true><<<1, 32, 0, st>>>(d->nhc, d->peer, seq, p->par.step_size);
+        else
+            nhc_peer_kernel<false><<<1, 32, 0, st>>>(d->nhc, d->peer, seq, p->par.step_size);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return VVB200_OK;
+    }
     if (p->par.cos_acceleration != 0)
         nhc_kernel<true><<<1, 32, 0, st>>>(p->dev->nhc, p->par.step_size);
     else
@@ -1126,6 +1209,50 @@ extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffer
     p->launches++;
     profMark(p->dev, 3, st);
     return vvb200_update_image_positions(p, b, stream);
+}
+
+extern "C" int vvb200_peer_export(vvb200_plan *p, void *handleOut64) {
+    if (!p || !p->dev || !handleOut64) {
+        vvb200_set_error("vvb200_peer_export: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    vvb200_device_state *d = p->dev;
+    if (!d->peerLocal) {
+        CUDA_TRY(cudaMalloc((void **) &d->peerLocal, sizeof(PeerSlots)));
+        d->allocations.push_back(d->peerLocal);
+        CUDA_TRY(cudaMemset(d->peerLocal, 0, sizeof(PeerSlots)));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, d->peerLocal));
+    memcpy(handleOut64, &h, sizeof h);
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_peer_attach(vvb200_plan *p, int rank, int world, const void *handles) {
+    if (!p || !p->dev || !handles || world < 1 || world > VVB200_MAX_RANKS || rank < 0 || rank >= world || !p->dev->peerLocal) {
+        vvb200_set_error("vvb200_peer_attach: invalid argument (world <= %d, vvb200_peer_export first)", VVB200_MAX_RANKS);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    vvb200_device_state *d = p->dev;
+    memset(&d->peer, 0, sizeof d->peer);
+    d->peer.rank = rank;
+    d->peer.world = world;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) {
+            d->peer.buf[r] = d->peerLocal;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *) handles + 64 * r, sizeof h);
+        void *mapped = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+        d->peerMapped.push_back(mapped);
+        d->peer.buf[r] = (PeerSlots *) mapped;
+    }
+    d->peerSeq = 0;
+    d->peerAttached = world > 1;
+    return VVB200_OK;
 }
 
 extern "C" int vvb200_partials_ptr(vvb200_plan *p, void **ptr, int32_t *n) {

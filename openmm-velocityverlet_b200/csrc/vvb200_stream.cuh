@@ -51,11 +51,11 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smemAddr(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
 }
 // global -> shared bulk copy (TMA engine, SASS UBLKCP), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulkLoad(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {

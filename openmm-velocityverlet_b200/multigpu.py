@@ -66,9 +66,31 @@ class DistributedPlan:
         self.plan.set_global_thermostat(self.dof, self.total_mass)
         self._red = None
 
-    def upload(self, stream=None):
+    def upload(self, stream=None, peer=None):
+        """peer=None: use the NVLink peer-memory exchange when the ranks can map each other's buffers (one node, cudaIpc),
+        else NCCL; peer=False forces NCCL; peer=True raises if peer mapping fails."""
         import torch
+        import torch.distributed as dist
         self.plan.upload(stream)
+        self.peer = False
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1 and peer is not False and world <= 8:
+            ok = 1
+            try:
+                mine = torch.from_numpy(self.plan.peer_export()).cuda()
+                gathered = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(gathered, mine, group=self.group)
+                handles = torch.stack(gathered).cpu().numpy()
+                self.plan.peer_attach(dist.get_rank(self.group), world, handles)
+            except Exception:
+                if peer:
+                    raise
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+            self.peer = bool(flag.item())
+            if not self.peer and ok:
+                self.plan.peer_attach(0, 1, self.plan.peer_export())           # detach: back to the NCCL path
         ptr, cnt = self.plan.partials()
 
         class _DevPtr:
@@ -80,6 +102,7 @@ class DistributedPlan:
     def step_middle(self, bufs, **kw):
         import torch.distributed as dist
         self.plan.middle_kick_reduce(bufs, **kw)
-        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self._red, group=self.group)           # the only exchange: <= 10 doubles
+        if not self.peer and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self._red, group=self.group)           # NCCL: the only exchange, <= 10 doubles
+        # peer path: the exchange happens inside the single-block NH-chain kernel, over cudaIpc-mapped NVLink memory
         self.plan.middle_nhc_scale_drift(bufs, **kw)

@@ -43,7 +43,10 @@ def main():
         lf = np.zeros((3, P), np.int64)
         lf[:, : b - a] = host.force[:, a:b]
         lstate = vv.HostState("mixed", cut(host.posq), cut(host.corr), cut(host.velm), lf, host.random, host.box)
-        dp = vv.DistributedPlan(local_spec, params, "mixed").upload()
+        mode = os.environ.get("VVB200_EXCHANGE", "auto")
+        dp = vv.DistributedPlan(local_spec, params, "mixed").upload(peer={"auto": None, "nccl": False, "peer": True}[mode])
+        if rank == 0:
+            print(f"[{name}] exchange: {'NVLink peer memory inside the NHC kernel' if dp.peer else 'NCCL all-reduce'}", flush=True)
         bufs = vv.DeviceBuffers(lstate)
         for _ in range(steps):
             dp.step_middle(bufs, inv_box_z=inv_box_z)
