@@ -1,0 +1,39 @@
+"""compute-sanitizer driver (not collected by pytest): runs every kernel family once on small systems.
+    compute-sanitizer --tool memcheck python tests/sanitize_gpu.py
+    compute-sanitizer --tool racecheck python tests/sanitize_gpu.py"""
+import dataclasses
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+vv = entry.load_package()
+EV = 1.60217662e-22
+import torch  # noqa: E402
+
+P = vv.Params
+bulk = vv.make_bulk_ionic_liquid(40)
+edl = vv.make_edl(n_ion_pairs=12, n_electrode=120, electrode_molecules=3)
+poly = vv.make_polymer(1, 600, 10)
+cases = [(bulk, P(max_drude_distance=0.02), {}), (bulk, P(max_drude_distance=0.02, cos_acceleration=0.02), dict(cos=True)),
+         (edl, P(max_drude_distance=0.02, mirror_location=1.2, electric_field=0.25 * EV), dict(n_random=4 * 122 * 4, mirror=1.2)),
+         (poly, P(max_drude_distance=0.02), {})]
+for spec, params, kw in cases:
+    for middle in (True, False):
+        for mode in ("mixed", "single", "double"):
+            if mode != "mixed" and spec.image_pairs.size:
+                continue
+            kw2 = dict(kw)
+            cos = kw2.pop("cos", False)
+            par = dataclasses.replace(params.resolved_for(spec), use_middle_scheme=middle)
+            host = vv.make_state(spec, mode, **kw2)
+            plan = vv.Plan(spec, par, mode).upload()
+            bufs = vv.DeviceBuffers(host, with_pos_delta=True)
+            plan.step(bufs, steps=2, inv_box_z=1.0 / host.box[2] if cos else 0.0)
+            if middle and not spec.langevin.size:
+                plan.middle_kick(bufs); plan.middle_delta(bufs, 0); plan.thermostat(bufs); plan.middle_delta(bufs, 1); plan.middle_finish(bufs)
+            torch.cuda.synchronize()
+            print("ok", spec.name, mode, "middle" if middle else "vv", "tiled" if plan.tiled else "general", flush=True)
+print("sanitize driver done")

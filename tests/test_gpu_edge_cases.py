@@ -1,0 +1,170 @@
+"""Edge cases of the CUDA path through the C ABI: sizes that are not multiples of anything, one-particle and
+one-pair systems, systems without a thermostat, without Drude particles, massless sites, step-size changes,
+thermostat-state save / restore (the reference loses its chain state on resume), error returns."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from conftest import TIGHT_HARDWALL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def both(vv, vo, spec, params, precision="mixed", steps=3, **kw):
+    host = vv.make_state(spec, precision, **kw)
+    plan = vv.Plan(spec, params, precision).upload()
+    bufs = vv.DeviceBuffers(host)
+    plan.step(bufs, steps=steps)
+    got = bufs.to_host()
+    oracle = vo.Oracle(spec, params, precision, literal=False)
+    want = host.copy()
+    oracle.step(want, steps=steps)
+    n = spec.n
+    assert rel_err(got.velm[:n, :3], want.velm[:n, :3]) <= TIGHT_HARDWALL[precision]
+    assert rel_err(got.positions()[:n], want.positions()[:n]) <= TIGHT_HARDWALL[precision]
+    return plan, oracle, got, want
+
+
+def tiny(vv, masses, pairs=(), mol=None, **kw):
+    n = len(masses)
+    bonds = [(p, d) for d, p in pairs]
+    spec = vv.SystemSpec(n=n, masses=np.array(masses, float), bonds=np.array(bonds, np.int32).reshape(-1, 2),
+                         drude_pairs=np.array(pairs, np.int32).reshape(-1, 2), **kw)
+    return spec.finalize(mol_id=None if mol is None else np.array(mol, np.int32))
+
+
+@pytest.mark.parametrize("precision", ["mixed", "double", "single"])
+def test_single_particle(vv, vo, precision):
+    spec = tiny(vv, [12.0])
+    params = vv.Params().resolved_for(spec)
+    if precision == "single":
+        host = vv.make_state(spec, precision)
+        plan = vv.Plan(spec, params, precision).upload()
+        bufs = vv.DeviceBuffers(host)
+        plan.step(bufs, steps=2)
+        assert np.isfinite(bufs.to_host().velm).all()
+    else:
+        both(vv, vo, spec, params, precision)
+
+
+def test_single_drude_pair(vv, vo):
+    spec = tiny(vv, [11.6, 0.4], pairs=[(1, 0)])
+    both(vv, vo, spec, vv.Params(max_drude_distance=0.02).resolved_for(spec))
+
+
+@pytest.mark.parametrize("n_ip", [1, 3, 7, 13, 14, 28])
+def test_sizes_around_tile_boundaries(vv, vo, n_ip):
+    """37 n particles: tiles end at odd indices, bulk copies start at unaligned slots"""
+    spec = vv.make_bulk_ionic_liquid(n_ip)
+    plan, *_ = both(vv, vo, spec, vv.Params(max_drude_distance=0.02).resolved_for(spec))
+    ts = plan.int_array("tileStart")
+    assert ts[-1] == 37 * n_ip
+
+
+def test_odd_monatomic_box(vv, vo):
+    """1,001 monatomic ions: 128 molecules per tile cap, every molecule a single particle (atom group has 0 DOF)"""
+    spec = tiny(vv, [35.45] * 1001)
+    params = dataclasses.replace(vv.Params(), use_com_temp_group=True)
+    plan, *_ = both(vv, vo, spec, params)
+    assert np.all(np.diff(plan.int_array("tileStart")) <= 128)
+
+
+def test_no_thermostat_all_langevin(vv, vo):
+    spec = vv.make_nonpolar_box(50, 5, has_cmm=False)
+    spec = dataclasses.replace(spec, langevin=np.arange(spec.n, dtype=np.int32)).finalize(mol_id=spec.mol_id)
+    params = dataclasses.replace(vv.Params(), use_com_temp_group=False)
+    plan, *_ = both(vv, vo, spec, params, n_random=4 * (spec.n + 2))
+    assert plan.int_array("particlesNH").size == 0
+
+
+def test_massless_sites_and_virtual_like_particles(vv, vo):
+    masses = [15.999, 1.008, 1.008, 0.0] * 40            # TIP4P-like: a massless site in every molecule
+    mol = np.repeat(np.arange(40), 4)
+    spec = tiny(vv, masses, mol=mol)
+    both(vv, vo, spec, dataclasses.replace(vv.Params(), use_com_temp_group=True))
+
+
+def test_step_size_change_is_picked_up(vv, vo):
+    spec = vv.make_bulk_ionic_liquid(20)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed")
+    plan = vv.Plan(spec, params, "mixed").upload()
+    bufs = vv.DeviceBuffers(host)
+    plan.step(bufs, steps=2)
+    plan.set_step_size(0.0005)
+    plan.step(bufs, steps=2)
+    got = bufs.to_host()
+    want = host.copy()
+    o1 = vo.Oracle(spec, params, "mixed", literal=False)
+    o1.step(want, steps=2)
+    st = o1.thermostat_state()
+    p2 = dataclasses.replace(params, step_size=0.0005)
+    o2 = vo.Oracle(spec, p2, "mixed", literal=False)
+    o2.lib.vvo_set_nhc_state(o2.h, st["eta"].ctypes.data, st["eta_dot"].ctypes.data, st["eta_dotdot"].ctypes.data)
+    o2.step(want, steps=2)
+    n = spec.n
+    assert rel_err(got.velm[:n, :3], want.velm[:n, :3]) <= 1e-8
+
+
+def test_thermostat_state_save_restore(vv, vo):
+    """4 steps == 2 steps, save chain state, fresh plan, restore, 2 steps (bitwise)"""
+    spec = vv.make_bulk_ionic_liquid(40)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed")
+    a = vv.DeviceBuffers(host)
+    pa = vv.Plan(spec, params, "mixed").upload()
+    pa.step(a, steps=4)
+    b = vv.DeviceBuffers(host)
+    pb = vv.Plan(spec, params, "mixed").upload()
+    pb.step(b, steps=2)
+    st = pb.thermostat_state()
+    mid = b.to_host()
+    pc = vv.Plan(spec, params, "mixed").upload()
+    pc.set_thermostat_state(st["eta"], st["eta_dot"], st["eta_dotdot"])
+    c = vv.DeviceBuffers(mid)
+    pc.step(c, steps=2)
+    ha, hc = a.to_host(), c.to_host()
+    assert np.array_equal(ha.velm, hc.velm) and np.array_equal(ha.posq, hc.posq) and np.array_equal(ha.corr, hc.corr)
+
+
+def test_error_returns(vv):
+    import torch
+    spec = vv.make_edl(n_ion_pairs=4, n_electrode=30, electrode_molecules=3)
+    params = vv.Params(mirror_location=1.0).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", n_random=200, mirror=1.0)
+    plan = vv.Plan(spec, params, "mixed")
+    bufs = vv.DeviceBuffers(host)
+    with pytest.raises(vv.VVB200Error) as e:
+        plan.step_middle(bufs)                              # not uploaded
+    assert e.value.code == 5
+    plan.upload()
+    bufs.corr = None
+    with pytest.raises(vv.VVB200Error) as e:
+        plan.step_middle(bufs)                              # mixed mode needs posqCorrection
+    assert e.value.code == 1
+    bufs = vv.DeviceBuffers(host)
+    bufs.random = None
+    with pytest.raises(vv.VVB200Error) as e:
+        plan.step_middle(bufs)                              # Langevin particles but no random buffer
+    assert e.value.code == 1 and "random" in e.value.message
+    bufs = vv.DeviceBuffers(host)
+    with pytest.raises(vv.VVB200Error):
+        plan.middle_finish(bufs)                            # no posDelta
+    with pytest.raises(vv.VVB200Error):
+        plan.step_host(host, steps=1)                       # host entry point refuses Langevin systems
+    torch.cuda.synchronize()
+
+
+def test_viscosity_and_launch_count(vv, vo):
+    spec = vv.make_bulk_ionic_liquid(30)
+    params = vv.Params(cos_acceleration=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed")
+    plan = vv.Plan(spec, params, "mixed").upload()
+    v0, iv0 = plan.viscosity(host.box)
+    assert v0 == 0.0 and iv0 == 0.0                         # defined before the first step (the reference's is not)
+    bufs = vv.DeviceBuffers(host)
+    plan.step(bufs, steps=2, inv_box_z=1.0 / host.box[2])
+    assert plan.launch_count == 4                           # 2 launches per step, no host sync
+    v, iv = plan.viscosity(host.box)
+    assert v != 0.0 and np.isfinite(iv)
