@@ -342,6 +342,14 @@ static bool buildTiles(vvb200_plan *p) {
         return useCOM && molIsNH[p->particleMolId[i]] && (p->masses[i] != 0.0 || p->isNH[i]);
     };
 
+    // the fused kernels take sum m|v - V|^2 as sum m|v|^2 - M|V|^2, which needs every massive member of a thermostat
+    // molecule to be a thermostat particle itself (a massive image particle would not be)
+    if (useCOM)
+        for (int i = 0; i < N; i++)
+            if (molIsNH[p->particleMolId[i]] && p->masses[i] != 0.0 && !p->isNH[i]) {
+                p->tiledWhyNot = "a massive particle outside the thermostat belongs to a thermostat molecule";
+                return false;
+            }
     std::vector<int32_t> lo(M, N), hi(M, -1);
     for (int i = 0; i < N; i++)
         if (comMember(i)) {

@@ -90,8 +90,6 @@ template <int MODE, bool EXTRA> struct PublishedA {
 template <int MODE, bool EXTRA> struct ScratchA {
     typedef typename Prec<MODE>::mixed mixed;
     PublishedA<MODE, EXTRA> pub[2];
-    mixed Vx[MAXMOL], Vy[MAXMOL], Vz[MAXMOL];
-    mixed cbar[EXTRA ? MAXMOL : 1];
     double red[CTHREADS / 32][VVB200_NRED];
     unsigned int ticket;
 };
@@ -261,6 +259,18 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
                     if (cosine && v.w != 0)   // cosineAccelerate.cu:26
                         acc[3] += mass * v.x * 2 * cph;
                 }
+                // Atom-group energy of a normal particle (drudeNoseHoover.cu:76-83).  The reference sums m|v - V_mol|^2;
+                // here sum m|v|^2 is taken per particle and M|V_mol|^2 subtracted once per molecule in phase 2 (the
+                // same number up to fp64 reassociation: every massive member of a thermostat molecule is in the sum),
+                // so no particle has to wait for its molecule's V.
+                if (!p.kickOnly && (meta[it] & VVB200_META_NH) && v.w != 0 &&
+                    ((meta[it] >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_NONE) {
+                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
+                    if (cosine) {
+                        acc[4] += v.x * cph * mass;
+                        acc[7] += cph * cph * mass;
+                    }
+                }
             }
         }
         if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
@@ -318,70 +328,50 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
                     mixed4 V;
                     V.w = vv_recip(comMass);
                     V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
-                    sm.Vx[j] = V.x; sm.Vy[j] = V.y; sm.Vz[j] = V.z;
                     st_stream(comV + mol, V);
-                    mixed cb = 0;
+                    // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w; the same amount
+                    // leaves the atom group (see phase 1)
+                    const mixed mv2 = (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
+                    acc[1] += mv2;
+                    acc[0] -= mv2;
                     if (cosine) {
-                        cb = sc * V.w;
-                        sm.cbar[j] = cb;
+                        const mixed cb = sc * V.w;
                         comCbar[mol] = cb;
-                    }
-                    // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w
-                    acc[1] += (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
-                    if (cosine) {
-                        acc[5] += comMass * V.x * cb;
-                        acc[8] += comMass * cb * cb;
+                        const mixed b = comMass * V.x * cb, c = comMass * cb * cb;
+                        acc[5] += b; acc[4] -= b;
+                        acc[8] += c; acc[7] -= c;
                     }
                 }
             }
-            consumerBarrier();
         }
 
-        // ---- phase 3: group kinetic energies of the COM-normalised velocities ------------------
+        // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: pair-COM term of
+        //      the atom group (in absolute velocities, see phase 1) and the relative-motion (Drude) group ----------
 #pragma unroll
         for (int it = 0; it < ITEMS; it++) {
             const uint32_t mw = meta[it];
-            if (!(mw & VVB200_META_NH)) continue;
+            if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
+                continue;
             const int loc = it * CTHREADS + tid;
-            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
-            const uint32_t lm = mw & VVB200_META_MOL_MASK;
-            mixed Vx = 0, Vy = 0, Vz = 0, cb = 0;
-            if (useCOM && lm != VVB200_META_MOL_NONE) {
-                Vx = sm.Vx[lm]; Vy = sm.Vy[lm]; Vz = sm.Vz[lm];
-                if (cosine) cb = sm.cbar[lm];
-            }
+            const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
             const mixed4 v = vel[it];     // .w = mass
-            if (role == VVB200_ROLE_NONE) {
-                if (v.w != 0) {   // drudeNoseHoover.cu:76-83: |u|^2 / w
-                    const mixed ux = v.x - Vx, uy = v.y - Vy, uz = v.z - Vz;
-                    acc[0] += (ux * ux + uy * uy + uz * uz) * v.w;
-                    if (cosine) {
-                        const mixed d = pub.cph[loc] - cb;
-                        acc[4] += ux * d * v.w;
-                        acc[7] += d * d * v.w;
-                    }
-                }
-            } else if (role == VVB200_ROLE_DRUDE) {   // drudeNoseHoover.cu:99-114; this thread owns the pair
-                const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-                const mixed mass1 = v.w, mass2 = pub.m[ploc];
-                const mixed u1x = v.x - Vx, u1y = v.y - Vy, u1z = v.z - Vz;
-                const mixed u2x = pub.vx[ploc] - Vx, u2y = pub.vy[ploc] - Vy, u2z = pub.vz[ploc] - Vz;
-                const mixed totalMass = mass1 + mass2;
-                const mixed invTotalMass = vv_recip(totalMass);
-                const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
-                const mixed redMass = mass1 * m2f;       // = 1 / ((m1+m2) w1 w2)
-                const mixed cmx = u1x * m1f + u2x * m2f, cmy = u1y * m1f + u2y * m2f, cmz = u1z * m1f + u2z * m2f;
-                const mixed rx = u1x - u2x, ry = u1y - u2y, rz = u1z - u2z;
-                acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
-                acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
-                if (cosine) {
-                    const mixed d1 = pub.cph[loc] - cb, d2 = pub.cph[ploc] - cb;
-                    const mixed cmd = d1 * m1f + d2 * m2f, rd = d1 - d2;
-                    acc[4] += cmx * cmd * totalMass;
-                    acc[7] += cmd * cmd * totalMass;
-                    acc[6] += rx * rd * redMass;
-                    acc[9] += rd * rd * redMass;
-                }
+            const mixed mass1 = v.w, mass2 = pub.m[ploc];
+            const mixed v2x = pub.vx[ploc], v2y = pub.vy[ploc], v2z = pub.vz[ploc];
+            const mixed totalMass = mass1 + mass2;
+            const mixed invTotalMass = vv_recip(totalMass);
+            const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
+            const mixed redMass = mass1 * m2f;       // = 1 / ((m1+m2) w1 w2)
+            const mixed cmx = v.x * m1f + v2x * m2f, cmy = v.y * m1f + v2y * m2f, cmz = v.z * m1f + v2z * m2f;
+            const mixed rx = v.x - v2x, ry = v.y - v2y, rz = v.z - v2z;
+            acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
+            acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
+            if (cosine) {
+                const mixed c1 = pub.cph[loc], c2 = pub.cph[ploc];
+                const mixed cmd = c1 * m1f + c2 * m2f, rd = c1 - c2;
+                acc[4] += cmx * cmd * totalMass;
+                acc[7] += cmd * cmd * totalMass;
+                acc[6] += rx * rd * redMass;
+                acc[9] += rd * rd * redMass;
             }
         }
         buf ^= 1;
