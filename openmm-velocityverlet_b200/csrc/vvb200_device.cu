@@ -1,26 +1,23 @@
-// vvb200_device.cu -- hand-written sm_100a kernels + device-side plan state + C-ABI step calls.
+// vvb200_device.cu -- device-side plan state, the small kernels, launch configuration and the C-ABI step calls.
 //
-// Design: the reference's 10-16 launches per step collapse
-// into two streaming passes over the particle arrays, both working on molecule-aligned tiles:
+// Design: the reference's 10-16 launches per step collapse into two
+// streaming passes over the particle arrays, both working on molecule-aligned tiles (vvb200_stream.cuh):
 //
-//   pass A  kick_reduce_kernel   velm += dt*w*(F + Fextra)   [integrateMiddleVel, middle.cu:6;
-//           extra forces computed inline: drudeLangevin.cu:2 (via the compact ldForce array),
-//           electricField.cu:2, cosineAccelerate.cu:2]; per-molecule COM velocity
-//           [calcCOMVelocities, drudeNoseHoover.cu:5] from shared memory in the reference's
-//           summation order; group kinetic energies of the COM-normalised velocities
-//           [normalizeVelocities :37 + computeNormalizedKineticEnergies :55] and the velocity-bias
-//           moments [calcPeriodicVelocityBias, cosineAccelerate.cu:16]; deterministic two-level
-//           reduction [replaces sumNormalizedKineticEnergies :121 and sumV :34]; the LAST block
-//           advances the Nose-Hoover chains on the device [VVIntegrator::propagateNHChain,
-//           VVIntegrator.cpp:340-376] -- no D2H/H2D round trip (CudaVVKernels.cpp:709-746).
-//   pass B  scale_drift_kernel   thermostat scaling [scaleVelocity, drudeNoseHoover.cu:157], bias
-//           remove/restore [cosineAccelerate.cu:63,76], both half drifts and the double-float
-//           position write [integrateMiddlePos1/2/3, middle.cu:29-100], Drude hard wall
-//           [applyHardWallConstraints, middle.cu:106].
+//   pass A  kick_reduce_kernel   velm += dt*w*(F + Fextra)   [integrateMiddleVel, middle.cu:6; extra forces computed
+//           inline: drudeLangevin.cu:2 (via the compact ldForce array), electricField.cu:2, cosineAccelerate.cu:2];
+//           per-molecule COM velocity [calcCOMVelocities, drudeNoseHoover.cu:5]; group kinetic energies
+//           [normalizeVelocities :37 + computeNormalizedKineticEnergies :55] and the velocity-bias moments
+//           [calcPeriodicVelocityBias, cosineAccelerate.cu:16]; deterministic two-level reduction [replaces
+//           sumNormalizedKineticEnergies :121 and sumV :34]; the LAST block advances the Nose-Hoover chains on the
+//           device [VVIntegrator::propagateNHChain, VVIntegrator.cpp:340-376] -- no D2H/H2D round trip
+//           (CudaVVKernels.cpp:709-746).
+//   pass B  scale_drift_kernel   thermostat scaling [scaleVelocity, drudeNoseHoover.cu:157], bias remove/restore
+//           [cosineAccelerate.cu:63,76], both half drifts and the double-float position write
+//           [integrateMiddlePos1/2/3, middle.cu:29-100], Drude hard wall [applyHardWallConstraints, middle.cu:106].
 //
-// velm (mixed4 = 32 B in mixed/double mode) moves with single 256-bit LDG/STG instructions, a
-// Blackwell (sm_100) addition.  All sums are fp64 (`mixed`) in a fixed order: results are bitwise
-// reproducible run to run.
+// Systems that cannot be tiled run the thermostat through the gather kernels of vvb200_general.cuh; multi-GPU runs
+// exchange the reduction vector inside nhc_peer_kernel (below).  All sums are fp64 (`mixed`) in a fixed order:
+// results are bitwise reproducible run to run.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1133,7 +1130,6 @@ static int withPosDelta(vvb200_plan *p, const vvb200_buffers *b, vvb200_buffers 
 extern "C" int vvb200_middle_delta(vvb200_plan *p, const vvb200_buffers *b, int accumulate, void *stream);
 extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, void *stream);
 extern "C" int vvb200_vv_positions(vvb200_plan *p, const vvb200_buffers *b, void *stream);
-template <int MODE> __global__ void vv_delta_kernel(const void *, void *, int, double);
 
 static int generalKick(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, int kick, bool extraForces,
                        cudaStream_t st) {
