@@ -30,4 +30,5 @@ from .system import (  # noqa: F401
     np_dtypes,
 )
 from .buffers import DeviceBuffers  # noqa: F401
+from .integrator import Context, OpenMMException, System, VVIntegrator  # noqa: F401
 from .multigpu import DistributedPlan, global_thermostat, partition_by_molecules  # noqa: F401
