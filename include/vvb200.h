@@ -212,6 +212,10 @@ int vvb200_set_global_thermostat(vvb200_plan *plan, const double *dof3, double t
  *                 ModifyCosineAccelerateKernel::applyCosineForce are folded into the kick. */
 int vvb200_middle_kick(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);      /* integrateMiddleVel, CudaVVKernels.cpp:144-148 */
 int vvb200_thermostat(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);       /* calc/removeVelocityBias + scaleVelocity + restoreVelocityBias */
+/* thermostat + integrateMiddlePos1 + integrateMiddlePos2 fused (one reduction pass + one scaling pass that also
+ * writes posDelta = oldDelta = dt/2 v + dt/2 v'): what the glue calls between OpenMM's velocity and position
+ * constraints.  kick (88 B) + this (32 + 128 B) + finish (192 B) = 440 B/particle, the constrained-path minimum. */
+int vvb200_middle_thermostat_delta(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);
 /* accumulate == 0: integrateMiddlePos1 (posDelta = oldDelta = dt/2 v, :154-158); != 0: integrateMiddlePos2 (+=, :169-173) */
 int vvb200_middle_delta(vvb200_plan *plan, const vvb200_buffers *buf, int accumulate, void *stream);
 int vvb200_middle_finish(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);                                  /* integrateMiddlePos3 + applyHardWallConstraints, :179-212 */

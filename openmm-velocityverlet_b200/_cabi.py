@@ -138,7 +138,7 @@ def load_library(path=None):
     lib.vvb200_plan_upload.argtypes = [vp, vp]
     for name in ("vvb200_step_middle", "vvb200_step_vv_first", "vvb200_step_vv_second",
                  "vvb200_middle_kick_reduce", "vvb200_middle_nhc_scale_drift", "vvb200_middle_kick",
-                 "vvb200_thermostat"):
+                 "vvb200_thermostat", "vvb200_middle_thermostat_delta"):
         getattr(lib, name).argtypes = [vp, P(_Buffers), P(_StepArgs), vp]
     lib.vvb200_middle_delta.argtypes = [vp, P(_Buffers), C.c_int, vp]
     lib.vvb200_middle_finish.argtypes = [vp, P(_Buffers), vp]
@@ -295,6 +295,9 @@ class Plan:
 
     def middle_kick(self, bufs, **kw):
         self._call(self.lib.vvb200_middle_kick, bufs, **kw)
+
+    def middle_thermostat_delta(self, bufs, **kw):
+        self._call(self.lib.vvb200_middle_thermostat_delta, bufs, **kw)
 
     def thermostat(self, bufs, **kw):
         self._call(self.lib.vvb200_thermostat, bufs, **kw)

@@ -12,7 +12,7 @@
 //   secondIntegrate                                               vvb200_middle_nhc_scale_drift  (NH chains + pass B)
 //   updateImagePositions                                          vvb200_update_image_positions
 // With constraints or virtual sites OpenMM's solvers must run between the sub-steps, so the split entry points are
-// used: kick -> applyVelocityConstraints -> delta(0) | thermostat | delta(1) -> applyConstraints -> finish.
+// used: kick -> applyVelocityConstraints | (no-op) | thermostat_delta -> applyConstraints -> finish  (440 B/particle).
 // Velocity-Verlet scheme: thermostat | vv_kick(+posDelta) -> applyConstraints -> vv_positions | vv_kick | thermostat.
 #include "CudaVVKernelsB200.h"
 
@@ -194,7 +194,6 @@ void CudaIntegrateMiddleStepKernel::firstIntegrate(ContextImpl &, const VVIntegr
     }
     VVB200_CHECK(vvb200_middle_kick(sh->plan, &b, &a, cu.getCurrentStream()));
     cu.getIntegrationUtilities().applyVelocityConstraints(integrator.getConstraintTolerance());
-    VVB200_CHECK(vvb200_middle_delta(sh->plan, &b, 0, cu.getCurrentStream()));
 }
 
 void CudaIntegrateMiddleStepKernel::secondIntegrate(ContextImpl &, const VVIntegrator &integrator) {
@@ -205,7 +204,8 @@ void CudaIntegrateMiddleStepKernel::secondIntegrate(ContextImpl &, const VVInteg
     if (!sh->constrained) {
         VVB200_CHECK(vvb200_middle_nhc_scale_drift(sh->plan, &b, &a, cu.getCurrentStream()));
     } else {
-        VVB200_CHECK(vvb200_middle_delta(sh->plan, &b, 1, cu.getCurrentStream()));
+        // thermostat (bias remove / restore included) + both half drifts into posDelta / oldDelta, fused
+        VVB200_CHECK(vvb200_middle_thermostat_delta(sh->plan, &b, &a, cu.getCurrentStream()));
         integration.applyConstraints(integrator.getConstraintTolerance());
         VVB200_CHECK(vvb200_middle_finish(sh->plan, &b, cu.getCurrentStream()));
     }
@@ -259,8 +259,8 @@ void CudaModifyDrudeNoseKernel::initialize(const System &, const VVIntegrator &,
 }
 
 void CudaModifyDrudeNoseKernel::scaleVelocity(ContextImpl &, const VVIntegrator &integrator) {
-    if (integrator.getUseMiddleScheme() && !sh->constrained)
-        return;                             // fused into pass A / pass B (see the table at the top)
+    if (integrator.getUseMiddleScheme())
+        return;                             // fused into the passes secondIntegrate launches (see the table at the top)
     ContextSelector selector(cu);
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);

@@ -117,6 +117,7 @@ struct KParams {
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
     void *posq, *corr, *velm;
+    void *posDelta, *oldDelta;   // VAR_SCALE_DELTA only
     const long long *force;
     const void *ldForce;
     void *comV;            // mixed4 per molecule
@@ -131,7 +132,7 @@ struct KParams {
 };
 
 enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
-enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2 };
+enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2, VAR_SCALE_DELTA = 3 };
 
 // tileMolInfo word: bits 0-10 first slot in tile, bits 11-21 count, bit 31 = not contiguous
 #define MOLINFO_FIRST(w) ((w) & 0x7FF)
@@ -1376,6 +1377,48 @@ extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const 
     return VVB200_OK;
 }
 
+extern "C" int vvb200_middle_delta(vvb200_plan *p, const vvb200_buffers *b, int accumulate, void *stream);
+
+static int ensureOldDelta(vvb200_plan *p, cudaStream_t st) {
+    vvb200_device_state *d = p->dev;
+    if (!d->oldDelta) {
+        const size_t bytes = (size_t) p->paddedN * 4 * mixedSize(p->precision);
+        CUDA_TRY(cudaMalloc(&d->oldDelta, bytes));
+        d->allocations.push_back(d->oldDelta);
+        CUDA_TRY(cudaMemsetAsync(d->oldDelta, 0, bytes, st));
+    }
+    return VVB200_OK;
+}
+
+// scaleVelocity + integrateMiddlePos1 + integrateMiddlePos2 in one go for systems with OpenMM constraints
+// (CudaVVKernels.cpp:154-173, 670-754): thermostat, then posDelta = oldDelta = dt/2 v + dt/2 v'
+extern "C" int vvb200_middle_thermostat_delta(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_middle_thermostat_delta", false, false);
+    if (rc) return rc;
+    if (!b->pos_delta) {
+        vvb200_set_error("vvb200_middle_thermostat_delta: pos_delta buffer required");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    if ((rc = ensureOldDelta(p, st))) return rc;
+    if (!p->tiled) {
+        if ((rc = vvb200_middle_delta(p, b, 0, stream))) return rc;
+        if (hasNH(p) && (rc = generalThermostat(p, b, a, true, true, true, st))) return rc;
+        return vvb200_middle_delta(p, b, 1, stream);
+    }
+    const bool cosine = p->par.cos_acceleration != 0;
+    KParams k = makeParams(p, b, a);
+    k.posDelta = b->pos_delta;
+    k.oldDelta = p->dev->oldDelta;
+    if (hasNH(p)) {
+        CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
+        p->launches++;
+    }
+    CUDA_TRY((dispatchB<VAR_SCALE_DELTA>(p->precision, cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    return VVB200_OK;
+}
+
 static int elementwiseGrid(const vvb200_plan *p, int n) {
     return std::max(1, std::min((n + THREADS - 1) / THREADS, p->dev->numSM * 8));
 }
@@ -1389,11 +1432,7 @@ extern "C" int vvb200_middle_delta(vvb200_plan *p, const vvb200_buffers *b, int 
     }
     cudaStream_t st = (cudaStream_t) stream;
     vvb200_device_state *d = p->dev;
-    if (!d->oldDelta) {
-        CUDA_TRY(cudaMalloc(&d->oldDelta, (size_t) p->paddedN * 4 * mixedSize(p->precision)));
-        d->allocations.push_back(d->oldDelta);
-        CUDA_TRY(cudaMemsetAsync(d->oldDelta, 0, (size_t) p->paddedN * 4 * mixedSize(p->precision), st));
-    }
+    if ((rc = ensureOldDelta(p, st))) return rc;
     const int grid = elementwiseGrid(p, p->N);
     switch (p->precision) {
     case VVB200_SINGLE: delta_kernel<VVB200_SINGLE><<<grid, THREADS, 0, st>>>(b->velm, b->pos_delta, d->oldDelta, p->N, p->par.step_size, accumulate); break;

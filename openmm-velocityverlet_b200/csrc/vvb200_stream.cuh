@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
 // pass B: thermostat scaling + bias remove/restore + drifts + position write + hard wall
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int VARIANT, bool EXTRA> struct StageB {
-    static constexpr bool POS = VARIANT != VAR_SCALE_ONLY;
+    static constexpr bool POS = VARIANT != VAR_SCALE_ONLY && VARIANT != VAR_SCALE_DELTA;
     static constexpr bool POSQ = POS || EXTRA;
     static constexpr bool CORR = POS && Prec<MODE>::kMixed;
     static constexpr bool FORCE = VARIANT == VAR_VV_FIRST;
@@ -691,6 +691,24 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
                 if (writeVel) {
                     mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
                     st_stream(velm + idx, o);
+                }
+                continue;
+            }
+            if (VARIANT == VAR_SCALE_DELTA) {
+                // integrateMiddlePos1 + Pos2 (middle.cu:33-41, 51-59): posDelta = oldDelta = dt/2 v0 + dt/2 v', for
+                // OpenMM's position constraints to work on before vvb200_middle_finish
+                if (writeVel) {
+                    mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                    st_stream(velm + idx, o);
+                }
+                if (ws != 0) {
+                    mixed4 d;
+                    d.x = halfdt * vs0[0]; d.x += halfdt * vs[0];
+                    d.y = halfdt * vs0[1]; d.y += halfdt * vs[1];
+                    d.z = halfdt * vs0[2]; d.z += halfdt * vs[2];
+                    d.w = 0;
+                    st_stream(reinterpret_cast<mixed4 *>(p.posDelta) + idx, d);
+                    st_stream(reinterpret_cast<mixed4 *>(p.oldDelta) + idx, d);
                 }
                 continue;
             }

@@ -312,3 +312,25 @@ def test_cuda_graph_capture_replays_the_step(vv, vo):
     assert np.array_equal(ha.velm, hb.velm) and np.array_equal(ha.posq, hb.posq) and np.array_equal(ha.corr, hb.corr)
     sa, sb = eager_plan.thermostat_state(), graph_plan.thermostat_state()
     assert np.array_equal(sa["eta_dot"], sb["eta_dot"])
+
+
+@pytest.mark.parametrize("cos", [False, True])
+def test_constrained_flow_matches_fused(vv, vo, cos):
+    """the 440 B/particle flow the glue uses when OpenMM constraints exist -- kick | thermostat_delta | finish, with
+    OpenMM's solvers between them -- is bitwise the fused step when nothing is constrained"""
+    import torch
+    spec = vv.make_bulk_ionic_liquid(120)
+    params = vv.Params(max_drude_distance=0.02, cos_acceleration=0.02 if cos else 0.0).resolved_for(spec)
+    host = vv.make_state(spec, "mixed")
+    inv_box_z = 1.0 / host.box[2] if cos else 0.0
+    pa, pb = vv.Plan(spec, params, "mixed").upload(), vv.Plan(spec, params, "mixed").upload()
+    a, b = vv.DeviceBuffers(host), vv.DeviceBuffers(host, with_pos_delta=True)
+    for _ in range(3):
+        pa.step_middle(a, inv_box_z=inv_box_z)
+        pb.middle_kick(b, inv_box_z=inv_box_z)
+        pb.middle_thermostat_delta(b, inv_box_z=inv_box_z)
+        pb.middle_finish(b)
+    torch.cuda.synchronize()
+    ha, hb = a.to_host(), b.to_host()
+    assert np.array_equal(hb.velm, ha.velm) and np.array_equal(hb.posq, ha.posq) and np.array_equal(hb.corr, ha.corr)
+    assert pb.launch_count == 3 * 5          # kick, reduce, scale+delta, finish, hard wall
