@@ -522,12 +522,20 @@ __global__ void hardwall_pairs_kernel(void *posqRaw, void *corrRaw, void *velmRa
     real4 *corr = reinterpret_cast<real4 *>(corrRaw);
     mixed4 *velm = reinterpret_cast<mixed4 *>(velmRaw);
     const mixed stepSize = (mixed) dt, maxD = (mixed) maxDrudeDistance, hwScale = (mixed) hardwallScale;
+    const real maxD2safe = (real) (maxDrudeDistance * maxDrudeDistance * (1.0 - 1e-4));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPairs; i += blockDim.x * gridDim.x) {
         const int2 pr = pairs[i];
         real4 q1 = posq[pr.x], q2 = posq[pr.y];
+        real4 c1, c2;
+        c1.x = c1.y = c1.z = c1.w = 0;
+        c2 = c1;
+        if (P::kMixed) { c1 = corr[pr.x]; c2 = corr[pr.y]; }
+        // conservative pre-test in `real` arithmetic (see pass B): most pairs are nowhere near the wall
+        const real sx = (q1.x - q2.x) + (c1.x - c2.x), sy = (q1.y - q2.y) + (c1.y - c2.y), sz = (q1.z - q2.z) + (c1.z - c2.z);
+        if (sx * sx + sy * sy + sz * sz < maxD2safe)
+            continue;
         mixed pos1[3] = {(mixed) q1.x, (mixed) q1.y, (mixed) q1.z}, pos2[3] = {(mixed) q2.x, (mixed) q2.y, (mixed) q2.z};
         if (P::kMixed) {
-            const real4 c1 = corr[pr.x], c2 = corr[pr.y];
             pos1[0] += (mixed) c1.x; pos1[1] += (mixed) c1.y; pos1[2] += (mixed) c1.z;
             pos2[0] += (mixed) c2.x; pos2[1] += (mixed) c2.y; pos2[2] += (mixed) c2.z;
         }
@@ -1349,15 +1357,17 @@ extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, co
 // ---- the VVKernels.h interfaces one by one (constraint-bearing path) ----------------------------
 extern "C" int vvb200_middle_kick(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
     // extra forces + integrateMiddleVel; the reductions that ride along are discarded because OpenMM's
-    // applyVelocityConstraints runs next (CudaVVKernels.cpp:144-151)
-    if (p && p->dev && !p->tiled) {
-        int rc = checkStepArgs(p, b, "vvb200_middle_kick", false, true);
-        if (rc) return rc;
-        cudaStream_t st = (cudaStream_t) stream;
-        if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
-        return generalKick(p, b, a, KICK_MIDDLE, true, st);
-    }
-    return vvb200_middle_kick_reduce(p, b, a, stream);
+    // applyVelocityConstraints runs next (CudaVVKernels.cpp:144-151): the molecule / pair phases are skipped
+    int rc = checkStepArgs(p, b, "vvb200_middle_kick", false, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
+    KParams k = makeParams(p, b, a);
+    k.fuseNHC = 0;
+    k.kickOnly = 1;
+    CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, k.cosine, k, p->dev->numSM, st)));
+    p->launches++;
+    return VVB200_OK;
 }
 
 extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
