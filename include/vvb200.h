@@ -249,6 +249,14 @@ int vvb200_get_com_velocities(vvb200_plan *plan, void *host_out, void *stream);
 /* kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 int64_t vvb200_launch_count(const vvb200_plan *plan);
 
+/* Small systems (all tiles co-resident in shared memory, up to ~227k particles in mixed mode) run
+ * the whole thermostatted step -- what CudaVVKernels.cpp:144-185 + 670-754 do in 9-10 launches and
+ * a blocking host round trip -- as ONE launch with a grid barrier (csrc/vvb200_resident.cuh).
+ * mode: -1 = default (on unless the environment says VVB200_RESIDENT=0), 0 = always use the two
+ * streaming passes, 1 = on.  vvb200_resident_launch_count: how many steps took the resident path. */
+int vvb200_set_resident_mode(vvb200_plan *plan, int mode);
+int64_t vvb200_resident_launch_count(const vvb200_plan *plan);
+
 /* Optional per-kernel timing of the middle step for bench.py's roofline: CUDA events are recorded on
  * the launching stream around pass A (kick + reductions) and pass B (scale + drift + position write) for
  * up to max_steps steps (0 disables).  vvb200_profile_read synchronises on the last event, returns the

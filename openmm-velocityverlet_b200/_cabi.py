@@ -156,6 +156,9 @@ def load_library(path=None):
     lib.vvb200_launch_count.argtypes = [vp]
     lib.vvb200_launch_count.restype = i64
     lib.vvb200_step_host.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, vp]
+    lib.vvb200_set_resident_mode.argtypes = [vp, C.c_int]
+    lib.vvb200_resident_launch_count.argtypes = [vp]
+    lib.vvb200_resident_launch_count.restype = i64
     lib.vvb200_profile_enable.argtypes = [vp, C.c_int]
     lib.vvb200_profile_read.argtypes = [vp, P(dbl), P(dbl), P(i32)]
     if path in (LIB_PATH, os.environ.get("VVB200_LIB")):
@@ -256,6 +259,15 @@ class Plan:
     @property
     def launch_count(self):
         return int(self.lib.vvb200_launch_count(self.h))
+
+    @property
+    def resident_launch_count(self):
+        """steps that ran as ONE launch with the state resident in shared memory (small systems)"""
+        return int(self.lib.vvb200_resident_launch_count(self.h))
+
+    def set_resident_mode(self, mode):
+        """-1 default (on unless VVB200_RESIDENT=0), 0 streaming passes only, 1 on"""
+        _check(self.lib, self.lib.vvb200_set_resident_mode(self.h, int(mode)))
 
     def set_step_size(self, dt):
         _check(self.lib, self.lib.vvb200_set_step_size(self.h, dt))

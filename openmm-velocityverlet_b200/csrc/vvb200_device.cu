@@ -129,6 +129,9 @@ struct KParams {
     double efscale, accel, invBoxZ, maxDrudeDistance, hardwallScale;
     int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC, cosine, kickOnly;
     int stagesA, stagesB;
+    // single-launch resident kernel (vvb200_resident.cuh)
+    int tilesPerBlock, doReduce;
+    unsigned int *gridGen;   // generation word of its grid barrier
 };
 
 enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
@@ -144,45 +147,88 @@ __device__ __forceinline__ double cosPhase(double z, double invBoxZ) {
     return cos(2 * 3.1415926 * z * invBoxZ);
 }
 
-// VVIntegrator::propagateNHChain on the device (VVIntegrator.cpp:340-376)
-__device__ double nhcPropagate(NhcDevice *s, int g, double dt, double ke2) {
-    const int nc = s->nc, loops = s->loops;
-    double *eta = s->eta[g], *etaDot = s->etaDot[g], *etaDotDot = s->etaDotDot[g];
-    const double *Q = s->etaMass[g];
+// VVIntegrator::propagateNHChain on the device (VVIntegrator.cpp:340-376).  The chain state is pulled into
+// thread-local arrays first (independent loads, one L2 round trip) and written back at the end: working on the
+// global arrays in place serialises ~50 dependent L2 accesses (~0.13 us each) and was most of a small system's step.
+// NC > 0: chain length known at compile time, loops unrolled, state in registers (the common lengths 1..4);
+// NC == 0: any length up to VVB200_MAX_CHAINS from local memory.  Same operation order either way.
+template <int NC>
+__device__ __forceinline__ double nhcPropagateT(NhcDevice *s, int g, double dt, double ke2) {
+    constexpr int CAP = NC > 0 ? NC : VVB200_MAX_CHAINS;
+    const int nc = NC > 0 ? NC : s->nc;
+    const int loops = s->loops;
+    double eta[CAP], etaDot[CAP + 1], etaDotDot[CAP], Q[CAP];
+#pragma unroll
+    for (int k = 0; k < CAP; k++) {
+        if (k < nc) {
+            eta[k] = s->eta[g][k];
+            etaDot[k] = s->etaDot[g][k];
+            etaDotDot[k] = s->etaDotDot[g][k];
+            Q[k] = s->etaMass[g][k];
+        }
+    }
+    etaDot[nc] = s->etaDot[g][nc];
     const double target = s->NkbT[g];
+    const double kT = BOLTZ_D * s->tTarget[g];
     const double h2 = dt / loops / 2, h4 = h2 / 2, h8 = h4 / 2;
     double factor = 1.0, e = 0.0;
     etaDotDot[0] = (ke2 - target) / Q[0];
     for (int l = 0; l < loops; l++) {
-        for (int k = nc - 1; k >= 0; k--) {
-            e = exp(-h8 * etaDot[k + 1]);
-            etaDot[k] *= e;
-            etaDot[k] += etaDotDot[k] * h4;
-            etaDot[k] *= e;
+#pragma unroll
+        for (int k = CAP - 1; k >= 0; k--) {
+            if (k < nc) {
+                e = exp(-h8 * etaDot[k + 1]);
+                etaDot[k] *= e;
+                etaDot[k] += etaDotDot[k] * h4;
+                etaDot[k] *= e;
+            }
         }
         factor *= exp(-h2 * etaDot[0]);
-        for (int k = 0; k < nc; k++)
-            eta[k] += h2 * etaDot[k];
+#pragma unroll
+        for (int k = 0; k < CAP; k++)
+            if (k < nc) eta[k] += h2 * etaDot[k];
         etaDotDot[0] = (ke2 * factor * factor - target) / Q[0];
         etaDot[0] *= e;
         etaDot[0] += etaDotDot[0] * h4;
         etaDot[0] *= e;
-        for (int k = 1; k < nc; k++) {
-            e = exp(-h8 * etaDot[k + 1]);
-            etaDot[k] *= e;
-            etaDotDot[k] = (Q[k - 1] * etaDot[k - 1] * etaDot[k - 1] - BOLTZ_D * s->tTarget[g]) / Q[k];
-            etaDot[k] += etaDotDot[k] * h4;
-            etaDot[k] *= e;
+#pragma unroll
+        for (int k = 1; k < CAP; k++) {
+            if (k < nc) {
+                e = exp(-h8 * etaDot[k + 1]);
+                etaDot[k] *= e;
+                etaDotDot[k] = (Q[k - 1] * etaDot[k - 1] * etaDot[k - 1] - kT) / Q[k];
+                etaDot[k] += etaDotDot[k] * h4;
+                etaDot[k] *= e;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CAP; k++) {
+        if (k < nc) {
+            s->eta[g][k] = eta[k];
+            s->etaDot[g][k] = etaDot[k];
+            s->etaDotDot[g][k] = etaDotDot[k];
         }
     }
     return factor;
 }
 
+// not inlined: one copy for all kernels, and its registers / local arrays stay out of the streaming kernels' budget
+__device__ __noinline__ double nhcPropagate(NhcDevice *s, int g, double dt, double ke2) {
+    switch (s->nc) {
+    case 1: return nhcPropagateT<1>(s, g, dt, ke2);
+    case 2: return nhcPropagateT<2>(s, g, dt, ke2);
+    case 3: return nhcPropagateT<3>(s, g, dt, ke2);
+    case 4: return nhcPropagateT<4>(s, g, dt, ke2);
+    default: return nhcPropagateT<0>(s, g, dt, ke2);
+    }
+}
+
 // From the reduced sums to bias, group energies and scale factors (CudaVVKernels.cpp:709-746 moved
 // onto the device).  Called by threads 0..2 of one block; `red` must already be final.
 template <bool COS>
-__device__ void nhcFinish(NhcDevice *s, double dt, int g) {
-    const double *red = s->red;
+__device__ void nhcFinish(NhcDevice *s, double dt, int g, const double *red = nullptr) {
+    if (!red) red = s->red;      // callers that just summed the vector pass their shared-memory copy
     double V = 0.0;
     if (COS)
         V = red[3] * s->invMassTotal;
@@ -272,6 +318,7 @@ __global__ void nhc_peer_kernel(NhcDevice *s, const PeerCtx ctx, unsigned long l
 }
 
 #include "vvb200_stream.cuh"
+#include "vvb200_resident.cuh"
 #include "vvb200_general.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -638,7 +685,10 @@ struct vvb200_device_state {
     void *comV = nullptr, *comCbar = nullptr, *ldForce = nullptr;
     double *partials = nullptr;
     NhcDevice *nhc = nullptr;
-    unsigned int *counter = nullptr;
+    unsigned int *counter = nullptr;   // [0] arrival counter of the last-block reductions, [1] grid-barrier generation
+    int64_t residentLaunches = 0;
+    int residentMode = -1;
+    int residentMaxParticles = -1;     // -1: from the environment (VVB200_RESIDENT_MAX_PARTICLES, default 120000)             // -1: from the environment (VVB200_RESIDENT, default on), 0 off, 1 on
     bool extraForcesValid = false;   // VV scheme: forceExtra is zero until the first second half
     // optional per-kernel timing (vvb200_profile_*): events recorded on the launching stream
     bool profiling = false;
@@ -795,7 +845,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
 
     // per-block partial sums: sized for the largest persistent grid any instantiation may use
     if ((rc = uploadVec(d, &d->partials, nullptr, (size_t) d->numSM * VVB200_MAX_BLOCKS_PER_SM * VVB200_NRED, st))) return rc;
-    if ((rc = uploadVec(d, &d->counter, nullptr, 1, st))) return rc;
+    if ((rc = uploadVec(d, &d->counter, nullptr, 2, st))) return rc;
     NhcDevice h;
     fillNhcHost(p, h);
     if ((rc = uploadVec(d, &d->nhc, &h, 1, st))) return rc;
@@ -862,7 +912,7 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
     k.posq = b->posq; k.corr = b->posq_correction; k.velm = b->velm; k.force = b->force;
     k.ldForce = d->ldForce; k.comV = d->comV; k.comCbar = d->comCbar;
-    k.partials = d->partials; k.nhc = d->nhc; k.counter = d->counter;
+    k.partials = d->partials; k.nhc = d->nhc; k.counter = d->counter; k.gridGen = d->counter + 1;
     k.dt = p->par.step_size;
     k.efscale = p->par.electric_field * AVOGADRO_D;          // CudaVVKernels.cpp:978
     k.accel = p->par.cos_acceleration;                       // :1044
@@ -958,6 +1008,96 @@ static cudaError_t dispatchB(int precision, bool, const KParams &k, int numSM, c
     case 4: return launchB<VVB200_DOUBLE, VARIANT, false>(k, numSM, st);
     default: return launchB<VVB200_DOUBLE, VARIANT, true>(k, numSM, st);
     }
+}
+
+// ---- single-launch resident step (vvb200_resident.cuh) ------------------------------------------------------------
+// Returns 1 when launched, 0 when the system does not fit on chip (the caller falls back to the streaming kernels),
+// -1 on a CUDA error.  Geometry: one tile per block while all blocks are co-resident (2 per SM); beyond that several
+// tiles per block with one block per SM.  The grid never exceeds occupancy x SMs: the kernel has a grid barrier.
+template <int MODE, int KICK, int VARIANT, bool EXTRA>
+static int launchResident(KParams k, int numSM, cudaStream_t st) {
+    constexpr int MAXT = 8;
+    auto kernel = resident_step_kernel<MODE, KICK, VARIANT, EXTRA>;
+    static int maxOptin = [&] {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess)
+            v -= (int) ((fa.sharedSizeBytes + 127) / 128 * 128);   // static shared memory counts against the same limit
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v) != cudaSuccess) {
+            cudaGetLastError();
+            v = 48 * 1024;
+        }
+        return v;
+    }();
+    static int occCache[MAXT + 1] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+    auto smem = [](int T) { return smemBytesR<MODE, KICK, VARIANT, EXTRA>(T); };
+    auto occ = [&](int T) {
+        if (occCache[T] < 0) {
+            int o = 0;
+            if (smem(T) <= (size_t) maxOptin)
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, CTHREADS, smem(T));
+            occCache[T] = o;
+        }
+        return occCache[T];
+    };
+    if (k.numTiles < 1)
+        return 0;
+    int T = 1, grid = k.numTiles;
+    if (k.numTiles > occ(1) * numSM) {
+        T = (k.numTiles + numSM - 1) / numSM;
+        if (T > MAXT || occ(T) < 1)
+            return 0;
+        grid = (k.numTiles + T - 1) / T;
+    }
+    k.tilesPerBlock = T;
+    kernel<<<grid, CTHREADS, smem(T), st>>>(k);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+template <int KICK, int VARIANT>
+static int dispatchResident(int precision, const KParams &k, int numSM, cudaStream_t st) {
+    switch (precision * 2 + (needsExtra(k) ? 1 : 0)) {
+    case 0: return launchResident<VVB200_SINGLE, KICK, VARIANT, false>(k, numSM, st);
+    case 1: return launchResident<VVB200_SINGLE, KICK, VARIANT, true>(k, numSM, st);
+    case 2: return launchResident<VVB200_MIXED, KICK, VARIANT, false>(k, numSM, st);
+    case 3: return launchResident<VVB200_MIXED, KICK, VARIANT, true>(k, numSM, st);
+    case 4: return launchResident<VVB200_DOUBLE, KICK, VARIANT, false>(k, numSM, st);
+    default: return launchResident<VVB200_DOUBLE, KICK, VARIANT, true>(k, numSM, st);
+    }
+}
+
+static bool residentEnabled(const vvb200_plan *p) {
+    vvb200_device_state *d = p->dev;
+    if (d->residentMode < 0)
+        d->residentMode = envInt("VVB200_RESIDENT", 1) ? 1 : 0;
+    // measured on B200 (tests/diag_small.py): one launch wins up to ~100k particles; beyond that the streaming
+    // kernels' deeper load pipeline does (148k: 18.4 vs 21.5 us per step)
+    if (d->residentMaxParticles < 0)
+        d->residentMaxParticles = envInt("VVB200_RESIDENT_MAX_PARTICLES", 120000);
+    return d->residentMode == 1 && p->tiled && p->N <= d->residentMaxParticles;
+}
+
+// Tries the resident kernel for the pass-A<KICK> + pass-B<VARIANT> pair; *launched tells whether it ran.
+template <int KICK, int VARIANT>
+static int tryResident(vvb200_plan *p, KParams k, bool reduce, cudaStream_t st, bool *launched) {
+    *launched = false;
+    if (!residentEnabled(p))
+        return VVB200_OK;
+    k.doReduce = reduce ? 1 : 0;
+    k.fuseNHC = reduce ? 1 : 0;
+    const int r = dispatchResident<KICK, VARIANT>(p->precision, k, p->dev->numSM, st);
+    if (r < 0) {
+        vvb200_set_error("resident step kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return VVB200_ERR_CUDA;
+    }
+    if (r == 1) {
+        *launched = true;
+        p->launches++;
+        p->dev->residentLaunches++;
+    }
+    return VVB200_OK;
 }
 
 static int launchLangevin(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, cudaStream_t st) {
@@ -1291,6 +1431,14 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
     profMark(p->dev, 0, st);
+    bool resident = false;
+    if ((rc = tryResident<KICK_MIDDLE, VAR_MIDDLE>(p, k, hasNH(p), st, &resident))) return rc;
+    if (resident) {   // small system: the whole step ran as one launch; reported as "pass A", pass B = 0
+        profMark(p->dev, 1, st);
+        profMark(p->dev, 2, st);
+        profMark(p->dev, 3, st);
+        return vvb200_update_image_positions(p, b, stream);
+    }
     CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
     profMark(p->dev, 1, st);
@@ -1323,6 +1471,10 @@ extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, con
     }
     KParams k = makeParams(p, b, a);
     k.extraForces = p->dev->extraForcesValid ? 1 : 0;
+    bool resident = false;
+    if ((rc = tryResident<KICK_NONE, VAR_VV_FIRST>(p, k, hasNH(p), st, &resident))) return rc;
+    if (resident)
+        return vvb200_update_image_positions(p, b, stream);
     if (hasNH(p)) {
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
@@ -1345,6 +1497,12 @@ extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, co
     }
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
+    if (hasNH(p)) {      // without a thermostat the second half is the kick alone: one streaming launch already
+        bool resident = false;
+        if ((rc = tryResident<KICK_VV, VAR_SCALE_ONLY>(p, k, true, st, &resident))) return rc;
+        if (resident)
+            return VVB200_OK;
+    }
     CUDA_TRY((dispatchA<KICK_VV>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
     if (hasNH(p)) {
@@ -1380,6 +1538,10 @@ extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const 
     if (!p->tiled)
         return generalThermostat(p, b, a, true, true, true, st);
     KParams k = makeParams(p, b, a);
+    bool resident = false;
+    if ((rc = tryResident<KICK_NONE, VAR_SCALE_ONLY>(p, k, true, st, &resident))) return rc;
+    if (resident)
+        return VVB200_OK;
     CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
     CUDA_TRY((dispatchB<VAR_SCALE_ONLY>(p->precision, cosine, k, p->dev->numSM, st)));
@@ -1421,6 +1583,10 @@ extern "C" int vvb200_middle_thermostat_delta(vvb200_plan *p, const vvb200_buffe
     k.posDelta = b->pos_delta;
     k.oldDelta = p->dev->oldDelta;
     if (hasNH(p)) {
+        bool resident = false;
+        if ((rc = tryResident<KICK_NONE, VAR_SCALE_DELTA>(p, k, true, st, &resident))) return rc;
+        if (resident)
+            return VVB200_OK;
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
     }
@@ -1632,6 +1798,23 @@ extern "C" int vvb200_get_com_velocities(vvb200_plan *p, void *hostOut, void *st
     CUDA_TRY(cudaStreamSynchronize(st));
     return VVB200_OK;
 }
+
+#ifdef VVB200_TRACE
+extern "C" int vvb200_debug_trace(unsigned long long *out, int n) {
+    return (int) cudaMemcpyFromSymbol(out, g_vvb200Trace, sizeof(unsigned long long) * n);
+}
+#endif
+
+extern "C" int vvb200_set_resident_mode(vvb200_plan *p, int mode) {
+    if (!p || !p->dev || mode < -1 || mode > 1) {
+        vvb200_set_error("vvb200_set_resident_mode: plan not uploaded or mode outside -1..1");
+        return p && p->dev ? VVB200_ERR_INVALID_ARGUMENT : VVB200_ERR_NOT_UPLOADED;
+    }
+    p->dev->residentMode = mode;
+    return VVB200_OK;
+}
+
+extern "C" int64_t vvb200_resident_launch_count(const vvb200_plan *p) { return p && p->dev ? p->dev->residentLaunches : 0; }
 
 // ---- host-buffer entry point ---------------------------------------------------------------------
 extern "C" int vvb200_step_host(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, int steps, void *stream) {

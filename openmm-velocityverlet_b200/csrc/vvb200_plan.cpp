@@ -397,22 +397,50 @@ static bool buildTiles(vvb200_plan *p) {
     for (int i = 1; i <= N; i++)
         molBefore[i] += molBefore[i - 1];
 
-    p->tileStart.clear();
-    p->tileStart.push_back(0);
-    int32_t s = 0;
-    while (s < N) {
-        int32_t e = std::min(N, s + VVB200_TILE_CAP);
-        while (e > s + 1 && molBefore[e] - molBefore[s] > VVB200_TILE_MAX_MOLS)
-            e--;
-        while (e > s && e < N && cover[e] != 0)
-            e--;
-        if (e == s) {
-            p->tiledWhyNot = "a thermostat molecule or Drude pair spans more than one tile";
-            p->tileStart.clear();
-            return false;
+    // Tile size.  Large systems: VVB200_TILE_CAP (what the streaming kernels' stages hold).  Small systems are bound
+    // by the latency of each thread's dependent fp64 chain, not by bytes, so they are cut into more, smaller tiles --
+    // about one per co-resident block of the B200 (148 SMs x 2) -- which spreads the same work over more SMs.
+    int cap = VVB200_TILE_CAP;
+    {
+        const char *env = getenv("VVB200_SMALL_TILES");
+        if (!env || atoi(env) != 0) {
+            const int perBlock = (N + 2 * 148 - 1) / (2 * 148);
+            cap = std::min(VVB200_TILE_CAP, std::max(128, (perBlock + 31) / 32 * 32));
         }
-        p->tileStart.push_back(e);
-        s = e;
+    }
+    for (;;) {
+        p->tileStart.clear();
+        p->tileStart.push_back(0);
+        int32_t s = 0;
+        bool ok = true;
+        while (s < N) {
+            int32_t e = std::min(N, s + cap);
+            while (e > s + 1 && molBefore[e] - molBefore[s] > VVB200_TILE_MAX_MOLS)
+                e--;
+            while (e > s && e < N && cover[e] != 0)
+                e--;
+            if (e == s) {
+                ok = false;
+                break;
+            }
+            p->tileStart.push_back(e);
+            s = e;
+        }
+        // small tiles only pay while every tile still gets its own co-resident block (units that may not be split
+        // leave tiles partly empty, so the count can exceed N / cap): otherwise grow the tile and cut again
+        if (ok && cap < VVB200_TILE_CAP && (int) p->tileStart.size() - 1 > 2 * 148) {
+            cap += 32;
+            continue;
+        }
+        if (ok)
+            break;
+        if (cap < VVB200_TILE_CAP) {     // a molecule longer than the small tile: fall back to full-size tiles
+            cap = VVB200_TILE_CAP;
+            continue;
+        }
+        p->tiledWhyNot = "a thermostat molecule or Drude pair spans more than one tile";
+        p->tileStart.clear();
+        return false;
     }
     const int numTiles = (int) p->tileStart.size() - 1;
 

@@ -33,6 +33,20 @@
 static_assert(VVB200_TILE_CAP % CTHREADS == 0, "tile must be a multiple of the consumer count");
 static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
 
+// -DVVB200_TRACE (diagnostic builds only, tests/diag_trace.py): %globaltimer stamps of thread 0 of every block
+#ifdef VVB200_TRACE
+__device__ unsigned long long g_vvb200Trace[1024 * 8];
+__device__ __forceinline__ void traceMark(int i) {
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_vvb200Trace[blockIdx.x * 8 + i] = t;
+    }
+}
+#else
+#define traceMark(i) ((void) 0)
+#endif
+
 // ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
@@ -106,6 +120,316 @@ template <int MODE, bool EXTRA> constexpr size_t smemBytesA(int stages) {
 // ------------------------------------------------------------------------------------------------
 // pass A: extra forces + kick + molecular COM + group kinetic energies (+ bias moments) + NH chains
 // ------------------------------------------------------------------------------------------------
+// The per-tile work is written once (passAPhase1 / passAPhase23 / blockReduce / lastBlockFinish) and used by the
+// streaming kernel below and by the single-launch resident kernel (vvb200_resident.cuh).  RESIDENT = the kicked
+// velocities, molecular velocities and cosine means stay in the shared-memory stage for pass B of the same launch.
+template <int MODE> struct ACtx {
+    typedef typename Prec<MODE>::real real;
+    typedef typename Prec<MODE>::mixed mixed;
+    mixed stepSize, fscale;
+    real efscale, accel, invBoxZ;
+    bool cosine, useCOM;
+};
+
+template <int MODE, int KICK> __device__ __forceinline__ ACtx<MODE> makeACtx(const KParams &p, bool extra) {
+    typedef typename Prec<MODE>::real real;
+    typedef typename Prec<MODE>::mixed mixed;
+    ACtx<MODE> c;
+    c.stepSize = (mixed) p.dt;
+    // middle.cu:11-12 / CudaVVKernels.cpp:306
+    c.fscale = KICK == KICK_VV ? (mixed) (0.5 * p.dt / (double) 0x100000000) : c.stepSize / (mixed) 0x100000000;
+    c.efscale = (real) p.efscale;
+    c.accel = (real) p.accel;
+    c.invBoxZ = (real) p.invBoxZ;
+    c.cosine = extra && p.cosine;
+    c.useCOM = p.useCOM;
+    return c;
+}
+
+// ---- phase 1: extra forces, kick, store; publish v' and mass ----------------------------------------
+template <int MODE, int KICK, bool EXTRA, bool RESIDENT, class Stage>
+__device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &cx, Stage &st, PublishedA<MODE, EXTRA> &pub,
+                                            typename Prec<MODE>::mixed4 (&vel)[ITEMS],   // .w holds the MASS (0 for massless)
+                                            uint32_t (&meta)[ITEMS],
+                                            typename Prec<MODE>::mixed (&acc)[EXTRA ? VVB200_NRED : 3], const int tid) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
+    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
+    const mixed stepSize = cx.stepSize, fscale = cx.fscale;
+    const real efscale = cx.efscale, accel = cx.accel, invBoxZ = cx.invBoxZ;
+    const bool cosine = cx.cosine;
+    const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = cx.useCOM ? st.desc[3] : 0;
+    const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
+    (void) velm;
+    // ---- phase 1: extra forces, kick, store; publish v' and mass --------------------------------
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const int loc = it * CTHREADS + tid;
+        const int idx = t0 + loc, sl = sl0 + loc;
+        meta[it] = VVB200_META_MOL_NONE;
+        vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
+        if (idx < t1) {
+            meta[it] = st.meta[sl];
+            mixed4 v = st.velm[sl];
+            double cph = 0;
+            real q = 0;
+            if (EXTRA) {
+                const real4 pq = st.posq[sl];
+                q = pq.w;
+                if (cosine) cph = cosPhase((double) pq.z, (double) invBoxZ);
+            }
+            if (KICK != KICK_NONE && v.w != 0) {
+                const long long fx = st.f[0][sl], fy = st.f[1][sl], fz = st.f[2][sl];
+                if (EXTRA) {
+                    // forceExtra as the reference builds it: reset, += Langevin, += field, += cosine
+                    real ex = 0, ey = 0, ez = 0;
+                    if (p.extraForces) {
+                        if (p.hasLD && (meta[it] & VVB200_META_LD)) {
+                            const real3 f = ldForce[p.ldSlot[idx]];
+                            ex = f.x; ey = f.y; ez = f.z;
+                        }
+                        if (p.hasField) {
+                            const int cnt = (meta[it] >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
+                            for (int c = 0; c < cnt; c++)
+                                ez += efscale * q;                         // electricField.cu:10
+                        }
+                        if (cosine)   // cosineAccelerate.cu:9 (float += double unless double mode)
+                            ex = (real) (ex + accel * cph * vv_recip(v.w));
+                    }
+                    if (KICK == KICK_MIDDLE) {   // middle.cu:17-19
+                        v.x += stepSize * v.w * ex + fscale * v.w * fx;
+                        v.y += stepSize * v.w * ey + fscale * v.w * fy;
+                        v.z += stepSize * v.w * ez + fscale * v.w * fz;
+                    } else {                      // velocityVerlet.cu:19-21 (0.5 is a double literal)
+                        v.x += 0.5 * stepSize * v.w * ex + fscale * v.w * fx;
+                        v.y += 0.5 * stepSize * v.w * ey + fscale * v.w * fy;
+                        v.z += 0.5 * stepSize * v.w * ez + fscale * v.w * fz;
+                    }
+                } else {
+                    // forceExtra == 0: the reference's first product is an exact zero
+                    v.x += fscale * v.w * fx;
+                    v.y += fscale * v.w * fy;
+                    v.z += fscale * v.w * fz;
+                }
+                if constexpr (RESIDENT) st.velm[sl] = v;      // stays on chip for pass B
+                else st_stream(velm + idx, v);
+            }
+            const mixed mass = v.w != 0 ? vv_recip(v.w) : (mixed) 0;
+            vel[it] = v;
+            vel[it].w = mass;
+            pub.vx[loc] = v.x; pub.vy[loc] = v.y; pub.vz[loc] = v.z; pub.m[loc] = mass;
+            if (EXTRA) {
+                pub.cph[loc] = cph;
+                if (cosine && v.w != 0)   // cosineAccelerate.cu:26
+                    acc[3] += mass * v.x * 2 * cph;
+            }
+            // Atom-group energy of a normal particle (drudeNoseHoover.cu:76-83).  The reference sums m|v - V_mol|^2;
+            // here sum m|v|^2 is taken per particle and M|V_mol|^2 subtracted once per molecule in phase 2 (the
+            // same number up to fp64 reassociation: every massive member of a thermostat molecule is in the sum),
+            // so no particle has to wait for its molecule's V.
+            if (!p.kickOnly && (meta[it] & VVB200_META_NH) && v.w != 0 &&
+                ((meta[it] >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_NONE) {
+                acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
+                if (cosine) {
+                    acc[4] += v.x * cph * mass;
+                    acc[7] += cph * cph * mass;
+                }
+            }
+        }
+    }
+    if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
+}
+
+// ---- phases 2 and 3 (after a block barrier): molecular COM velocities, then the Drude pairs -----------
+template <int MODE, bool EXTRA, bool RESIDENT, class Stage>
+__device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> &cx, Stage &st, PublishedA<MODE, EXTRA> &pub,
+                                             const typename Prec<MODE>::mixed4 (&vel)[ITEMS], const uint32_t (&meta)[ITEMS],
+                                             typename Prec<MODE>::mixed (&acc)[EXTRA ? VVB200_NRED : 3], const int tid,
+                                             const int t0, const int t1, const int m0, const int nMol, const int molFirst) {
+    typedef Prec<MODE> P;
+    typedef typename P::mixed mixed;
+    typedef typename P::mixed4 mixed4;
+    mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
+    mixed *comCbar = reinterpret_cast<mixed *>(p.comCbar);
+    const bool cosine = cx.cosine;
+    (void) st;
+    // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30): COM_LANES lanes per
+    //      molecule stride over its particles, then a butterfly over the lane group (fixed order) ----
+    if (nMol > 0) {
+        const int grp = tid / COM_LANES, sub = tid % COM_LANES;
+        for (int jb = 0; jb < nMol; jb += CTHREADS / COM_LANES) {
+            const int j = jb + grp;
+            const bool active = j < nMol;
+            mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
+            uint32_t info = 0;
+            int mol = 0;
+            if (active) {
+                info = (uint32_t) pub.molInfo[j];
+                mol = molFirst >= 0 ? molFirst + j : p.tileMolList[m0 + j];
+                if (!MOLINFO_SCATTERED(info)) {
+                    const int first = MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
+                    for (int k = first + sub; k < first + cnt; k += COM_LANES) {
+                        const mixed mass = pub.m[k];        // 0 for massless particles: no contribution
+                        sx += pub.vx[k] * mass; sy += pub.vy[k] * mass; sz += pub.vz[k] * mass;
+                        if (cosine) sc += pub.cph[k] * mass;
+                        comMass += mass;
+                    }
+                } else if (sub == 0) {
+                    // members interleaved with other molecules: walk the sorted list (any topology)
+                    const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
+                    for (int k = 0; k < cnt; k++) {
+                        const int loc = p.sortedByMol[start + k] - t0;
+                        if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
+                        const mixed mass = pub.m[loc];
+                        sx += pub.vx[loc] * mass; sy += pub.vy[loc] * mass; sz += pub.vz[loc] * mass;
+                        if (cosine) sc += pub.cph[loc] * mass;
+                        comMass += mass;
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = COM_LANES / 2; off > 0; off >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                sy += __shfl_xor_sync(0xffffffffu, sy, off);
+                sz += __shfl_xor_sync(0xffffffffu, sz, off);
+                comMass += __shfl_xor_sync(0xffffffffu, comMass, off);
+                if (EXTRA) sc += __shfl_xor_sync(0xffffffffu, sc, off);
+            }
+            if (active && sub == 0) {
+                mixed4 V;
+                V.w = vv_recip(comMass);
+                V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
+                st_stream(comV + mol, V);
+                if constexpr (RESIDENT) st.comV[j] = V;
+                // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w; the same amount
+                // leaves the atom group (see phase 1)
+                const mixed mv2 = (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
+                acc[1] += mv2;
+                acc[0] -= mv2;
+                if (cosine) {
+                    const mixed cb = sc * V.w;
+                    comCbar[mol] = cb;
+                    if constexpr (RESIDENT) st.cbar[j] = cb;
+                    const mixed b = comMass * V.x * cb, c = comMass * cb * cb;
+                    acc[5] += b; acc[4] -= b;
+                    acc[8] += c; acc[7] -= c;
+                }
+            }
+        }
+    }
+
+    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: pair-COM term of
+    //      the atom group (in absolute velocities, see phase 1) and the relative-motion (Drude) group ----------
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const uint32_t mw = meta[it];
+        if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
+            continue;
+        const int loc = it * CTHREADS + tid;
+        const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+        const mixed4 v = vel[it];     // .w = mass
+        const mixed mass1 = v.w, mass2 = pub.m[ploc];
+        const mixed v2x = pub.vx[ploc], v2y = pub.vy[ploc], v2z = pub.vz[ploc];
+        const mixed totalMass = mass1 + mass2;
+        const mixed invTotalMass = vv_recip(totalMass);
+        const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
+        const mixed redMass = mass1 * m2f;       // = 1 / ((m1+m2) w1 w2)
+        const mixed cmx = v.x * m1f + v2x * m2f, cmy = v.y * m1f + v2y * m2f, cmz = v.z * m1f + v2z * m2f;
+        const mixed rx = v.x - v2x, ry = v.y - v2y, rz = v.z - v2z;
+        acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
+        acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
+        if (cosine) {
+            const mixed c1 = pub.cph[loc], c2 = pub.cph[ploc];
+            const mixed cmd = c1 * m1f + c2 * m2f, rd = c1 - c2;
+            acc[4] += cmx * cmd * totalMass;
+            acc[7] += cmd * cmd * totalMass;
+            acc[6] += rx * rd * redMass;
+            acc[9] += rd * rd * redMass;
+        }
+    }
+}
+
+// ---- per-block reduction of the thread accumulators (fixed order) and the arrival ticket: true for the block
+//      that arrives last.  All CTHREADS consumer threads call it. -------------------------------------------------
+template <int NR, class Scratch, class mixed>
+__device__ __forceinline__ bool blockReduceAndTicket(const KParams &p, Scratch &sm, const mixed (&acc)[NR], const int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        double v = (double) acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm.red[warp][k] = v;
+    }
+    consumerBarrier();
+    if (tid < VVB200_NRED) {
+        double v = 0;
+        if (tid < NR) {
+#pragma unroll
+            for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
+        }
+        p.partials[(size_t) blockIdx.x * VVB200_NRED + tid] = v;
+    }
+    __threadfence();
+    consumerBarrier();
+    if (tid == 0)
+        sm.ticket = atomicAdd(p.counter, 1u);
+    consumerBarrier();
+    return sm.ticket == gridDim.x - 1;
+}
+
+// ---- the last block sums the per-block partials block-major in a fixed order and advances the NH chains ---------
+// `work`: the thermostat state to advance -- p.nhc itself, or a shared-memory copy the caller prefetched and writes
+// back afterwards (resident kernel: saves the chain's serial L2 round trips).
+template <int NR, class Scratch>
+__device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, const bool cosine, const int tid,
+                                                NhcDevice *work = nullptr) {
+    if (!work) work = p.nhc;
+    const int lane = tid & 31, warp = tid >> 5;
+    __threadfence();
+    // all NR sums of a block's partials are fetched together (independent loads: one L2 round trip per block row)
+    double tot[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++) tot[k] = 0;
+    for (int b = tid; b < (int) gridDim.x; b += CTHREADS) {
+#pragma unroll
+        for (int k = 0; k < NR; k++)
+            tot[k] += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
+    }
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        double v = tot[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sm.red[warp][k] = v;
+    }
+    consumerBarrier();
+    if (tid < VVB200_NRED) {
+        double v = 0;
+        if (tid < NR)
+            for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
+        work->red[tid] = v;
+        sm.red[0][tid] = v;      // thread `tid` is the only reader of column `tid`
+    }
+    if (tid == 0)
+        *p.counter = 0;
+    consumerBarrier();
+#ifdef VVB200_TRACE
+    traceMark(7);
+#endif
+    if (p.fuseNHC && tid < 3) {
+        if (cosine) nhcFinish<true>(work, p.dt, tid, sm.red[0]);
+        else nhcFinish<false>(work, p.dt, tid, sm.red[0]);
+    }
+}
+
 template <int MODE, int KICK, bool EXTRA>
 __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(const KParams p) {
     typedef Prec<MODE> P;
@@ -168,19 +492,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
     }
 
     // ===== consumers =====
-    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
-    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
-    mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
-    mixed *comCbar = reinterpret_cast<mixed *>(p.comCbar);
-
-    const mixed stepSize = (mixed) p.dt;
-    // middle.cu:11-12 / CudaVVKernels.cpp:306
-    const mixed fscale = KICK == KICK_VV ? (mixed) (0.5 * p.dt / (double) 0x100000000)
-                                         : stepSize / (mixed) 0x100000000;
-    const real efscale = (real) p.efscale;
-    const real accel = (real) p.accel;
-    const real invBoxZ = (real) p.invBoxZ;
-
+    const ACtx<MODE> c = makeACtx<MODE, KICK>(p, EXTRA);
     constexpr int NR = EXTRA ? VVB200_NRED : 3;
     // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
     mixed acc[NR];
@@ -194,86 +506,9 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
         PublishedA<MODE, EXTRA> &pub = sm.pub[buf];
         const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
-        const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
-
-        mixed4 vel[ITEMS];       // .w holds the MASS from here on (0 for massless)
+        mixed4 vel[ITEMS];
         uint32_t meta[ITEMS];
-        // ---- phase 1: extra forces, kick, store; publish v' and mass --------------------------------
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const int loc = it * CTHREADS + tid;
-            const int idx = t0 + loc, sl = sl0 + loc;
-            meta[it] = VVB200_META_MOL_NONE;
-            vel[it].x = vel[it].y = vel[it].z = vel[it].w = 0;
-            if (idx < t1) {
-                meta[it] = st.meta[sl];
-                mixed4 v = st.velm[sl];
-                double cph = 0;
-                real q = 0;
-                if (EXTRA) {
-                    const real4 pq = st.posq[sl];
-                    q = pq.w;
-                    if (cosine) cph = cosPhase((double) pq.z, (double) invBoxZ);
-                }
-                if (KICK != KICK_NONE && v.w != 0) {
-                    const long long fx = st.f[0][sl], fy = st.f[1][sl], fz = st.f[2][sl];
-                    if (EXTRA) {
-                        // forceExtra as the reference builds it: reset, += Langevin, += field, += cosine
-                        real ex = 0, ey = 0, ez = 0;
-                        if (p.extraForces) {
-                            if (p.hasLD && (meta[it] & VVB200_META_LD)) {
-                                const real3 f = ldForce[p.ldSlot[idx]];
-                                ex = f.x; ey = f.y; ez = f.z;
-                            }
-                            if (p.hasField) {
-                                const int cnt = (meta[it] >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
-                                for (int c = 0; c < cnt; c++)
-                                    ez += efscale * q;                         // electricField.cu:10
-                            }
-                            if (cosine)   // cosineAccelerate.cu:9 (float += double unless double mode)
-                                ex = (real) (ex + accel * cph * vv_recip(v.w));
-                        }
-                        if (KICK == KICK_MIDDLE) {   // middle.cu:17-19
-                            v.x += stepSize * v.w * ex + fscale * v.w * fx;
-                            v.y += stepSize * v.w * ey + fscale * v.w * fy;
-                            v.z += stepSize * v.w * ez + fscale * v.w * fz;
-                        } else {                      // velocityVerlet.cu:19-21 (0.5 is a double literal)
-                            v.x += 0.5 * stepSize * v.w * ex + fscale * v.w * fx;
-                            v.y += 0.5 * stepSize * v.w * ey + fscale * v.w * fy;
-                            v.z += 0.5 * stepSize * v.w * ez + fscale * v.w * fz;
-                        }
-                    } else {
-                        // forceExtra == 0: the reference's first product is an exact zero
-                        v.x += fscale * v.w * fx;
-                        v.y += fscale * v.w * fy;
-                        v.z += fscale * v.w * fz;
-                    }
-                    st_stream(velm + idx, v);
-                }
-                const mixed mass = v.w != 0 ? vv_recip(v.w) : (mixed) 0;
-                vel[it] = v;
-                vel[it].w = mass;
-                pub.vx[loc] = v.x; pub.vy[loc] = v.y; pub.vz[loc] = v.z; pub.m[loc] = mass;
-                if (EXTRA) {
-                    pub.cph[loc] = cph;
-                    if (cosine && v.w != 0)   // cosineAccelerate.cu:26
-                        acc[3] += mass * v.x * 2 * cph;
-                }
-                // Atom-group energy of a normal particle (drudeNoseHoover.cu:76-83).  The reference sums m|v - V_mol|^2;
-                // here sum m|v|^2 is taken per particle and M|V_mol|^2 subtracted once per molecule in phase 2 (the
-                // same number up to fp64 reassociation: every massive member of a thermostat molecule is in the sum),
-                // so no particle has to wait for its molecule's V.
-                if (!p.kickOnly && (meta[it] & VVB200_META_NH) && v.w != 0 &&
-                    ((meta[it] >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_NONE) {
-                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
-                    if (cosine) {
-                        acc[4] += v.x * cph * mass;
-                        acc[7] += cph * cph * mass;
-                    }
-                }
-            }
-        }
-        if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
+        passAPhase1<MODE, KICK, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid);
         mbarArrive(empty + s);      // this thread no longer needs the stage: the producer may refill it
         if (++s == stages) { s = 0; phase ^= 1; }
         if (p.kickOnly) {           // any-topology path: the thermostat runs in the gather kernels
@@ -281,153 +516,13 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
             continue;
         }
         consumerBarrier();
-
-        // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30): COM_LANES lanes per
-        //      molecule stride over its particles, then a butterfly over the lane group (fixed order) ----
-        if (nMol > 0) {
-            const int grp = tid / COM_LANES, sub = tid % COM_LANES;
-            for (int jb = 0; jb < nMol; jb += CTHREADS / COM_LANES) {
-                const int j = jb + grp;
-                const bool active = j < nMol;
-                mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
-                uint32_t info = 0;
-                int mol = 0;
-                if (active) {
-                    info = (uint32_t) pub.molInfo[j];
-                    mol = molFirst >= 0 ? molFirst + j : p.tileMolList[m0 + j];
-                    if (!MOLINFO_SCATTERED(info)) {
-                        const int first = MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
-                        for (int k = first + sub; k < first + cnt; k += COM_LANES) {
-                            const mixed mass = pub.m[k];        // 0 for massless particles: no contribution
-                            sx += pub.vx[k] * mass; sy += pub.vy[k] * mass; sz += pub.vz[k] * mass;
-                            if (cosine) sc += pub.cph[k] * mass;
-                            comMass += mass;
-                        }
-                    } else if (sub == 0) {
-                        // members interleaved with other molecules: walk the sorted list (any topology)
-                        const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
-                        for (int k = 0; k < cnt; k++) {
-                            const int loc = p.sortedByMol[start + k] - t0;
-                            if (loc < 0 || loc >= t1 - t0) continue;   // massless non-thermostatted members elsewhere
-                            const mixed mass = pub.m[loc];
-                            sx += pub.vx[loc] * mass; sy += pub.vy[loc] * mass; sz += pub.vz[loc] * mass;
-                            if (cosine) sc += pub.cph[loc] * mass;
-                            comMass += mass;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int off = COM_LANES / 2; off > 0; off >>= 1) {
-                    sx += __shfl_xor_sync(0xffffffffu, sx, off);
-                    sy += __shfl_xor_sync(0xffffffffu, sy, off);
-                    sz += __shfl_xor_sync(0xffffffffu, sz, off);
-                    comMass += __shfl_xor_sync(0xffffffffu, comMass, off);
-                    if (EXTRA) sc += __shfl_xor_sync(0xffffffffu, sc, off);
-                }
-                if (active && sub == 0) {
-                    mixed4 V;
-                    V.w = vv_recip(comMass);
-                    V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
-                    st_stream(comV + mol, V);
-                    // molecular temperature group (drudeNoseHoover.cu:91-97): |V|^2 / comVelm.w; the same amount
-                    // leaves the atom group (see phase 1)
-                    const mixed mv2 = (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
-                    acc[1] += mv2;
-                    acc[0] -= mv2;
-                    if (cosine) {
-                        const mixed cb = sc * V.w;
-                        comCbar[mol] = cb;
-                        const mixed b = comMass * V.x * cb, c = comMass * cb * cb;
-                        acc[5] += b; acc[4] -= b;
-                        acc[8] += c; acc[7] -= c;
-                    }
-                }
-            }
-        }
-
-        // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: pair-COM term of
-        //      the atom group (in absolute velocities, see phase 1) and the relative-motion (Drude) group ----------
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const uint32_t mw = meta[it];
-            if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
-                continue;
-            const int loc = it * CTHREADS + tid;
-            const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-            const mixed4 v = vel[it];     // .w = mass
-            const mixed mass1 = v.w, mass2 = pub.m[ploc];
-            const mixed v2x = pub.vx[ploc], v2y = pub.vy[ploc], v2z = pub.vz[ploc];
-            const mixed totalMass = mass1 + mass2;
-            const mixed invTotalMass = vv_recip(totalMass);
-            const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
-            const mixed redMass = mass1 * m2f;       // = 1 / ((m1+m2) w1 w2)
-            const mixed cmx = v.x * m1f + v2x * m2f, cmy = v.y * m1f + v2y * m2f, cmz = v.z * m1f + v2z * m2f;
-            const mixed rx = v.x - v2x, ry = v.y - v2y, rz = v.z - v2z;
-            acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
-            acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
-            if (cosine) {
-                const mixed c1 = pub.cph[loc], c2 = pub.cph[ploc];
-                const mixed cmd = c1 * m1f + c2 * m2f, rd = c1 - c2;
-                acc[4] += cmx * cmd * totalMass;
-                acc[7] += cmd * cmd * totalMass;
-                acc[6] += rx * rd * redMass;
-                acc[9] += rd * rd * redMass;
-            }
-        }
+        passAPhase23<MODE, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst);
         buf ^= 1;
     }
 
-    // ---- block reduction (fixed order), then the last block finishes ----------------------------
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < NR; k++) {
-        double v = (double) acc[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0) sm.red[warp][k] = v;
-    }
-    consumerBarrier();
-    if (tid < VVB200_NRED) {
-        double v = 0;
-        if (tid < NR) {
-#pragma unroll
-            for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
-        }
-        p.partials[(size_t) blockIdx.x * VVB200_NRED + tid] = v;
-    }
-    __threadfence();
-    consumerBarrier();
-    if (tid == 0)
-        sm.ticket = atomicAdd(p.counter, 1u);
-    consumerBarrier();
-    if (sm.ticket != gridDim.x - 1)
+    if (!blockReduceAndTicket<NR>(p, sm, acc, tid))
         return;
-    // last block: sum the per-block partials block-major in a fixed order
-    __threadfence();
-    for (int k = 0; k < NR; k++) {
-        double v = 0;
-        for (int b = tid; b < (int) gridDim.x; b += CTHREADS)
-            v += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-            v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0) sm.red[warp][k] = v;
-    }
-    consumerBarrier();
-    if (tid < VVB200_NRED) {
-        double v = 0;
-        if (tid < NR)
-            for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
-        p.nhc->red[tid] = v;
-    }
-    if (tid == 0)
-        *p.counter = 0;
-    consumerBarrier();
-    if (p.fuseNHC && tid < 3) {
-        if (cosine) nhcFinish<true>(p.nhc, p.dt, tid);
-        else nhcFinish<false>(p.nhc, p.dt, tid);
-    }
+    lastBlockFinish<NR>(p, sm, cosine, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -476,6 +571,366 @@ __device__ __forceinline__ void splitPos(typename Prec<MODE>::mixed x, typename 
     lo = (real) (x - (typename Prec<MODE>::mixed) hi);
 }
 
+// Everything pass B needs besides the stage: step constants and this step's thermostat factors.
+template <int MODE> struct BCtx {
+    typedef typename Prec<MODE>::real real;
+    typedef typename Prec<MODE>::mixed mixed;
+    mixed stepSize, halfdt, invStepSize, fscaleVV, sA, sC, sD, Vb, maxD, hwScale;
+    real maxD2safe, efscale, accel, invBoxZ;
+    bool cosine, useCOM;
+    bool writeAllVel;   // resident kernel: pass A's kick is still in shared memory, every massive particle is written
+};
+
+// `nhc` values are read through L2 (__ldcg): in the resident kernel another block wrote them during this launch
+template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams &p, bool extra) {
+    typedef typename Prec<MODE>::real real;
+    typedef typename Prec<MODE>::mixed mixed;
+    BCtx<MODE> c;
+    c.cosine = extra && p.cosine;
+    c.useCOM = p.useCOM;
+    c.writeAllVel = false;
+    c.stepSize = (mixed) p.dt;
+    c.halfdt = 0.5f * c.stepSize;                       // middle.cu:33,51
+    c.invStepSize = (mixed) (1.0 / c.stepSize);         // velocityVerlet.cu:40
+    c.fscaleVV = (mixed) (0.5 * p.dt / (double) 0x100000000);
+    c.sA = (mixed) __ldcg(&p.nhc->vscale[0]);
+    c.sC = (mixed) __ldcg(&p.nhc->vscale[1]);
+    c.sD = (mixed) __ldcg(&p.nhc->vscale[2]);
+    c.Vb = c.cosine ? (mixed) __ldcg(&p.nhc->vBias) : (mixed) 0;
+    c.maxD = (mixed) p.maxDrudeDistance;
+    // conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold
+    c.maxD2safe = (real) (p.maxDrudeDistance * p.maxDrudeDistance * (1.0 - 1e-4));
+    c.hwScale = (mixed) p.hardwallScale;
+    c.efscale = (real) p.efscale;
+    c.accel = (real) p.accel;
+    c.invBoxZ = (real) p.invBoxZ;
+    return c;
+}
+
+// One tile of pass B from a filled stage (used by the streaming kernel below and the resident kernel).
+template <int MODE, int VARIANT, bool EXTRA, class Stage>
+__device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx, Stage &st, const int tid) {
+    typedef Prec<MODE> P;
+    typedef typename P::real real;
+    typedef typename P::mixed mixed;
+    typedef typename P::real4 real4;
+    typedef typename P::mixed4 mixed4;
+    typedef typename P::real3 real3;
+    constexpr bool POS = Stage::POS;
+    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
+    real4 *posq = reinterpret_cast<real4 *>(p.posq);
+    real4 *corr = reinterpret_cast<real4 *>(p.corr);
+    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
+    const mixed stepSize = cx.stepSize, halfdt = cx.halfdt, invStepSize = cx.invStepSize, fscaleVV = cx.fscaleVV;
+    const mixed sA = cx.sA, sC = cx.sC, sD = cx.sD, Vb = cx.Vb, maxD = cx.maxD, hwScale = cx.hwScale;
+    const real maxD2safe = cx.maxD2safe, efscale = cx.efscale, accel = cx.accel, invBoxZ = cx.invBoxZ;
+    const bool cosine = cx.cosine, useCOM = cx.useCOM;
+    (void) posq; (void) corr; (void) ldForce; (void) invStepSize; (void) fscaleVV; (void) efscale; (void) accel;
+    const int t0 = st.desc[0], t1 = st.desc[1], cbOff = st.desc[5];
+    const int sl0 = t0 - (t0 & ~3);
+
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const int loc = it * CTHREADS + tid;
+        const int idx = t0 + loc, sl = sl0 + loc;
+        if (idx >= t1) continue;
+        const uint32_t mw = st.meta[sl];
+        const mixed4 vel = st.velm[sl];
+        real4 pq;
+        pq.x = pq.y = pq.z = pq.w = 0;
+        mixed xs[3] = {0, 0, 0};
+        real4 cs;
+        cs.x = cs.y = cs.z = cs.w = 0;
+        if (Stage::POSQ) {
+            pq = st.posq[sl];
+            xs[0] = pq.x; xs[1] = pq.y; xs[2] = pq.z;
+            if (Stage::CORR) {
+                cs = st.corr[sl];
+                xs[0] = pq.x + (mixed) cs.x;       // middle.cu:82-84
+                xs[1] = pq.y + (mixed) cs.y;
+                xs[2] = pq.z + (mixed) cs.z;
+            }
+        }
+        double cphs = 0, cq = 0;
+        if (cosine) cphs = cosPhase((double) pq.z, (double) invBoxZ);
+
+        const bool isNH = mw & VVB200_META_NH;
+        const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
+        const uint32_t lm = mw & VVB200_META_MOL_MASK;
+        const int psl = sl + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+        const bool hasMol = useCOM && lm != VVB200_META_MOL_NONE;
+        mixed V[3] = {0, 0, 0};
+        mixed cb = 0;
+        if (hasMol) {
+            const mixed4 Vm = st.comV[lm];
+            V[0] = Vm.x; V[1] = Vm.y; V[2] = Vm.z;
+            if (cosine) cb = st.cbar[cbOff + lm];
+        }
+        // this particle ("s") and, for pair roles, its partner ("q")
+        mixed vs[3] = {vel.x, vel.y, vel.z};
+        const mixed ws = vel.w;
+        mixed vq[3] = {0, 0, 0}, wq = 0;
+        // the partner's position stays in its raw (posq, posqCorrection) form: it is only converted when the
+        // hard wall's pre-test cannot rule the wall out
+        real4 pqq, cqr;
+        pqq.x = pqq.y = pqq.z = pqq.w = 0;
+        cqr.x = cqr.y = cqr.z = cqr.w = 0;
+        mixed ds[3] = {0, 0, 0}, dq[3] = {0, 0, 0};      // position increments of this particle / its partner
+        if (role != VVB200_ROLE_NONE) {
+            const mixed4 v2 = st.velm[psl];
+            vq[0] = v2.x; vq[1] = v2.y; vq[2] = v2.z; wq = v2.w;
+            if (Stage::POSQ) {
+                pqq = st.posq[psl];
+                if (Stage::CORR) cqr = st.corr[psl];
+                if (cosine) cq = cosPhase((double) pqq.z, (double) invBoxZ);
+            }
+        }
+        // velocities entering the drift as "pre-thermostat" values (middle.cu:33-41)
+        const mixed vs0[3] = {vs[0], vs[1], vs[2]};
+        const mixed vq0[3] = {vq[0], vq[1], vq[2]};
+        bool writeVel = cx.writeAllVel && ws != 0;
+
+        if (isNH) {
+            // removePeriodicVelocityBias (cosineAccelerate.cu:63-71)
+            if (cosine) { vs[0] -= Vb * cphs; vq[0] -= Vb * cq; }
+            // bias-removed molecular velocity: V' = V - Vb*cbar e_x
+            mixed Vn[3] = {V[0], V[1], V[2]};
+            if (cosine && hasMol) Vn[0] = V[0] - Vb * cb;
+            if (hasMol) {   // normalizeVelocities, drudeNoseHoover.cu:42-48
+#pragma unroll
+                for (int d = 0; d < 3; d++) { vs[d] -= Vn[d]; vq[d] -= Vn[d]; }
+            }
+            if (role == VVB200_ROLE_NONE) {
+                if (ws != 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) vs[d] = sA * vs[d] + sC * Vn[d];   // drudeNoseHoover.cu:172-176
+                }
+                writeVel = cosine || hasMol || ws != 0;
+            } else {
+                // mass fractions m_k/(m1+m2) = w_other/(w1+w2): one division per pair member
+                const mixed invW = vv_recip(ws + wq);
+                const mixed fs = wq * invW, fq = ws * invW;
+                mixed o1[3], o2[3];
+                if (role == VVB200_ROLE_DRUDE) {
+                    scalePair<mixed>(vs, vq, fs, fq, Vn, sA, sC, sD, o1, o2);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { vs[d] = o1[d]; vq[d] = o2[d]; }
+                } else {
+                    scalePair<mixed>(vq, vs, fq, fs, Vn, sA, sC, sD, o1, o2);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) { vq[d] = o1[d]; vs[d] = o2[d]; }
+                }
+                writeVel = true;
+            }
+            if (cosine) { vs[0] += Vb * cphs; vq[0] += Vb * cq; }   // restorePeriodicVelocityBias
+        } else if (cosine) {
+            // non-thermostatted atoms still see remove then restore (cosineAccelerate.cu:63-84)
+            vs[0] -= Vb * cphs; vs[0] += Vb * cphs;
+            vq[0] -= Vb * cq; vq[0] += Vb * cq;
+            writeVel = true;
+        }
+
+        if (VARIANT == VAR_SCALE_ONLY) {
+            if (writeVel) {
+                mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                st_stream(velm + idx, o);
+            }
+            continue;
+        }
+        if (VARIANT == VAR_SCALE_DELTA) {
+            // integrateMiddlePos1 + Pos2 (middle.cu:33-41, 51-59): posDelta = oldDelta = dt/2 v0 + dt/2 v', for
+            // OpenMM's position constraints to work on before vvb200_middle_finish
+            if (writeVel) {
+                mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+                st_stream(velm + idx, o);
+            }
+            if (ws != 0) {
+                mixed4 d;
+                d.x = halfdt * vs0[0]; d.x += halfdt * vs[0];
+                d.y = halfdt * vs0[1]; d.y += halfdt * vs[1];
+                d.z = halfdt * vs0[2]; d.z += halfdt * vs[2];
+                d.w = 0;
+                st_stream(reinterpret_cast<mixed4 *>(p.posDelta) + idx, d);
+                st_stream(reinterpret_cast<mixed4 *>(p.oldDelta) + idx, d);
+            }
+            continue;
+        }
+
+        bool writePos = false;
+        if (VARIANT == VAR_VV_FIRST) {
+            // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
+            // particle and (redundantly) its partner
+            for (int who = 0; who < 2; who++) {
+                if (who == 1 && role == VVB200_ROLE_NONE) break;
+                const int js = who == 0 ? sl : psl;
+                mixed *v = who == 0 ? vs : vq;
+                const mixed w = who == 0 ? ws : wq;
+                if (w == 0) continue;
+                real ex = 0, ey = 0, ez = 0;
+                if (EXTRA && p.extraForces) {
+                    const uint32_t mj = who == 0 ? mw : st.meta[js];
+                    if (p.hasLD && (mj & VVB200_META_LD)) {
+                        const real3 f = ldForce[p.ldSlot[t0 + js - sl0]];
+                        ex = f.x; ey = f.y; ez = f.z;
+                    }
+                    if (p.hasField) {
+                        const int cnt = (mj >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
+                        const real q = who == 0 ? pq.w : pqq.w;
+                        for (int c = 0; c < cnt; c++) ez += efscale * q;
+                    }
+                    if (cosine) {
+                        const double c = who == 0 ? cphs : cq;
+                        ex = (real) (ex + accel * c * vv_recip(w));
+                    }
+                }
+                const long long fx = st.f[0][Stage::FORCE ? js : 0], fy = st.f[1][Stage::FORCE ? js : 0],
+                                fz = st.f[2][Stage::FORCE ? js : 0];
+                v[0] += 0.5 * stepSize * w * ex + fscaleVV * w * fx;
+                v[1] += 0.5 * stepSize * w * ey + fscaleVV * w * fy;
+                v[2] += 0.5 * stepSize * w * ez + fscaleVV * w * fz;
+            }
+            // posDelta = dt*v ; x += posDelta ; v = posDelta/dt  (velocityVerlet.cu:25,52-58)
+            if (ws != 0) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    ds[d] = stepSize * vs[d];
+                    xs[d] += ds[d];
+                    vs[d] = (mixed) (invStepSize * ds[d]);
+                }
+                writePos = writeVel = true;
+            }
+            if (role != VVB200_ROLE_NONE && wq != 0) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    dq[d] = stepSize * vq[d];
+                    vq[d] = (mixed) (invStepSize * dq[d]);
+                }
+            }
+        } else {
+            // middle scheme without constraints: posDelta = oldDelta = halfdt*v0 + halfdt*v', so
+            // integrateMiddlePos3 leaves v' unchanged and moves x by posDelta (middle.cu:33-98)
+            if (ws != 0) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    ds[d] = halfdt * vs0[d];
+                    ds[d] += halfdt * vs[d];
+                    xs[d] += ds[d];
+                }
+                writePos = writeVel = true;
+            }
+            if (role != VVB200_ROLE_NONE && wq != 0) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    dq[d] = halfdt * vq0[d];
+                    dq[d] += halfdt * vq[d];
+                }
+            }
+        }
+
+        // ---- Drude hard wall (middle.cu:114-220), evaluated by both members of the pair ----------
+        if (p.hardwall && role != VVB200_ROLE_NONE) {
+            // Pre-test in `real` arithmetic on the raw operands: the new separation is (posq_s - posq_q) +
+            // (corr_s - corr_q) + (ds - dq); the first difference is exact or off by < 4e-9 nm (neighbouring floats),
+            // so the squared distance is good to ~1e-6 relative and a 1e-4 margin is conservative.  Only a pair
+            // that might touch the wall pays for the partner's fp64 position and the reference's sqrt / reciprocal.
+            const real sx = (pq.x - pqq.x) + (cs.x - cqr.x) + (real) (ds[0] - dq[0]);
+            const real sy = (pq.y - pqq.y) + (cs.y - cqr.y) + (real) (ds[1] - dq[1]);
+            const real sz = (pq.z - pqq.z) + (cs.z - cqr.z) + (real) (ds[2] - dq[2]);
+            if (!(sx * sx + sy * sy + sz * sz < maxD2safe)) {
+                mixed xq[3] = {pqq.x + (mixed) cqr.x, pqq.y + (mixed) cqr.y, pqq.z + (mixed) cqr.z};
+#pragma unroll
+                for (int d = 0; d < 3; d++) xq[d] += dq[d];
+                // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
+                if (P::kMixed) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        real hi, lo;
+                        if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
+                        if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
+                    }
+                }
+                const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
+                mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
+                const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
+                const mixed d2 = dx * dx + dy * dy + dz * dz;
+                mixed *vel1 = selfIsDrude ? vs : vq, *vel2 = selfIsDrude ? vq : vs;
+                const mixed w1 = selfIsDrude ? ws : wq, w2 = selfIsDrude ? wq : ws;
+                const mixed r = vv_sqrt<MODE, mixed>(d2);
+                const mixed rInv = vv_recip(r);
+                if (rInv * maxD < 1) {
+                    const mixed bond[3] = {dx * rInv, dy * rInv, dz * rInv};
+                    const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
+                    const mixed deltaR = r - maxD;
+                    mixed deltaT = stepSize;
+                    mixed dotvr1 = vel1[0] * bond[0] + vel1[1] * bond[1] + vel1[2] * bond[2];
+                    mixed vp1[3];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) vp1[d] = vel1[d] - bond[d] * dotvr1;
+                    if (w2 == 0) {
+                        if (dotvr1 != 0) deltaT = deltaR / fabs(dotvr1);
+                        if (deltaT > stepSize) deltaT = stepSize;
+                        dotvr1 = -dotvr1 * hwScale / (fabs(dotvr1) * vv_sqrt<MODE, mixed>(mass1));
+                        const mixed dr = -deltaR + deltaT * dotvr1;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            pos1[d] += bond[d] * dr;
+                            vel1[d] = vp1[d] + bond[d] * dotvr1;
+                        }
+                    } else {
+                        const mixed invTotalMass = vv_recip(mass1 + mass2);
+                        mixed dotvr2 = vel2[0] * bond[0] + vel2[1] * bond[1] + vel2[2] * bond[2];
+                        mixed vp2[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) vp2[d] = vel2[d] - bond[d] * dotvr2;
+                        const mixed vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
+                        dotvr1 -= vbCMass;
+                        dotvr2 -= vbCMass;
+                        if (dotvr1 != dotvr2) deltaT = deltaR / fabs(dotvr1 - dotvr2);
+                        if (deltaT > stepSize) deltaT = stepSize;
+                        const mixed vBond = hwScale / vv_sqrt<MODE, mixed>(mass1);
+                        dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabs(dotvr1);
+                        dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabs(dotvr2);
+                        const mixed dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
+                        const mixed dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
+                        dotvr1 += vbCMass;
+                        dotvr2 += vbCMass;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            pos1[d] += bond[d] * dr1;
+                            pos2[d] += bond[d] * dr2;
+                            vel1[d] = vp1[d] + bond[d] * dotvr1;
+                            vel2[d] = vp2[d] + bond[d] * dotvr2;
+                        }
+                    }
+                    // the reference writes the touched members unconditionally (middle.cu:166-172, 204-219)
+                    if (selfIsDrude || w2 != 0) writePos = writeVel = true;
+                }
+            }
+        }
+
+        if (writeVel) {
+            mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
+            st_stream(velm + idx, o);
+        }
+        if (POS && writePos) {
+            real4 o;
+            if (P::kMixed) {
+                real4 oc;
+                splitPos<MODE>(xs[0], o.x, oc.x);
+                splitPos<MODE>(xs[1], o.y, oc.y);
+                splitPos<MODE>(xs[2], o.z, oc.z);
+                o.w = pq.w;
+                oc.w = 0;
+                st_stream(posq + idx, o);
+                st_stream(corr + idx, oc);
+            } else {
+                o.x = (real) xs[0]; o.y = (real) xs[1]; o.z = (real) xs[2]; o.w = pq.w;
+                st_stream(posq + idx, o);
+            }
+        }
+    }
+}
+
 template <int MODE, int VARIANT, bool EXTRA>
 __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(const KParams p) {
     typedef Prec<MODE> P;
@@ -485,7 +940,6 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     typedef typename P::mixed4 mixed4;
     typedef typename P::real3 real3;
     typedef StageB<MODE, VARIANT, EXTRA> Stage;
-    constexpr bool POS = Stage::POS;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int stages = p.stagesB;
     constexpr size_t stageBytes = roundUp128(sizeof(Stage));
@@ -559,333 +1013,13 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     }
 
     // ===== consumers =====
-    mixed4 *velm = reinterpret_cast<mixed4 *>(p.velm);
-    real4 *posq = reinterpret_cast<real4 *>(p.posq);
-    real4 *corr = reinterpret_cast<real4 *>(p.corr);
-    const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
-
-    const mixed stepSize = (mixed) p.dt;
-    const mixed halfdt = 0.5f * stepSize;                       // middle.cu:33,51
-    const mixed invStepSize = (mixed) (1.0 / stepSize);         // velocityVerlet.cu:40
-    const mixed fscaleVV = (mixed) (0.5 * p.dt / (double) 0x100000000);
-    const mixed sA = (mixed) p.nhc->vscale[0], sC = (mixed) p.nhc->vscale[1], sD = (mixed) p.nhc->vscale[2];
-    const mixed Vb = cosine ? (mixed) p.nhc->vBias : (mixed) 0;
-    const mixed maxD = (mixed) p.maxDrudeDistance;
-    // conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold
-    const real maxD2safe = (real) (p.maxDrudeDistance * p.maxDrudeDistance * (1.0 - 1e-4));
-    const mixed hwScale = (mixed) p.hardwallScale;
-    const real efscale = (real) p.efscale;
-    const real accel = (real) p.accel;
-    const real invBoxZ = (real) p.invBoxZ;
-
+    const BCtx<MODE> cx = makeBCtx<MODE>(p, EXTRA);
     int s = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
-        const int t0 = st.desc[0], t1 = st.desc[1], cbOff = st.desc[5];
-        const int sl0 = t0 - (t0 & ~3);
-
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const int loc = it * CTHREADS + tid;
-            const int idx = t0 + loc, sl = sl0 + loc;
-            if (idx >= t1) continue;
-            const uint32_t mw = st.meta[sl];
-            const mixed4 vel = st.velm[sl];
-            real4 pq;
-            pq.x = pq.y = pq.z = pq.w = 0;
-            mixed xs[3] = {0, 0, 0};
-            real4 cs;
-            cs.x = cs.y = cs.z = cs.w = 0;
-            if (Stage::POSQ) {
-                pq = st.posq[sl];
-                xs[0] = pq.x; xs[1] = pq.y; xs[2] = pq.z;
-                if (Stage::CORR) {
-                    cs = st.corr[sl];
-                    xs[0] = pq.x + (mixed) cs.x;       // middle.cu:82-84
-                    xs[1] = pq.y + (mixed) cs.y;
-                    xs[2] = pq.z + (mixed) cs.z;
-                }
-            }
-            double cphs = 0, cq = 0;
-            if (cosine) cphs = cosPhase((double) pq.z, (double) invBoxZ);
-
-            const bool isNH = mw & VVB200_META_NH;
-            const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
-            const uint32_t lm = mw & VVB200_META_MOL_MASK;
-            const int psl = sl + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-            const bool hasMol = useCOM && lm != VVB200_META_MOL_NONE;
-            mixed V[3] = {0, 0, 0};
-            mixed cb = 0;
-            if (hasMol) {
-                const mixed4 Vm = st.comV[lm];
-                V[0] = Vm.x; V[1] = Vm.y; V[2] = Vm.z;
-                if (cosine) cb = st.cbar[cbOff + lm];
-            }
-            // this particle ("s") and, for pair roles, its partner ("q")
-            mixed vs[3] = {vel.x, vel.y, vel.z};
-            const mixed ws = vel.w;
-            mixed vq[3] = {0, 0, 0}, wq = 0;
-            // the partner's position stays in its raw (posq, posqCorrection) form: it is only converted when the
-            // hard wall's pre-test cannot rule the wall out
-            real4 pqq, cqr;
-            pqq.x = pqq.y = pqq.z = pqq.w = 0;
-            cqr.x = cqr.y = cqr.z = cqr.w = 0;
-            mixed ds[3] = {0, 0, 0}, dq[3] = {0, 0, 0};      // position increments of this particle / its partner
-            if (role != VVB200_ROLE_NONE) {
-                const mixed4 v2 = st.velm[psl];
-                vq[0] = v2.x; vq[1] = v2.y; vq[2] = v2.z; wq = v2.w;
-                if (Stage::POSQ) {
-                    pqq = st.posq[psl];
-                    if (Stage::CORR) cqr = st.corr[psl];
-                    if (cosine) cq = cosPhase((double) pqq.z, (double) invBoxZ);
-                }
-            }
-            // velocities entering the drift as "pre-thermostat" values (middle.cu:33-41)
-            const mixed vs0[3] = {vs[0], vs[1], vs[2]};
-            const mixed vq0[3] = {vq[0], vq[1], vq[2]};
-            bool writeVel = false;
-
-            if (isNH) {
-                // removePeriodicVelocityBias (cosineAccelerate.cu:63-71)
-                if (cosine) { vs[0] -= Vb * cphs; vq[0] -= Vb * cq; }
-                // bias-removed molecular velocity: V' = V - Vb*cbar e_x
-                mixed Vn[3] = {V[0], V[1], V[2]};
-                if (cosine && hasMol) Vn[0] = V[0] - Vb * cb;
-                if (hasMol) {   // normalizeVelocities, drudeNoseHoover.cu:42-48
-#pragma unroll
-                    for (int d = 0; d < 3; d++) { vs[d] -= Vn[d]; vq[d] -= Vn[d]; }
-                }
-                if (role == VVB200_ROLE_NONE) {
-                    if (ws != 0) {
-#pragma unroll
-                        for (int d = 0; d < 3; d++) vs[d] = sA * vs[d] + sC * Vn[d];   // drudeNoseHoover.cu:172-176
-                    }
-                    writeVel = cosine || hasMol || ws != 0;
-                } else {
-                    // mass fractions m_k/(m1+m2) = w_other/(w1+w2): one division per pair member
-                    const mixed invW = vv_recip(ws + wq);
-                    const mixed fs = wq * invW, fq = ws * invW;
-                    mixed o1[3], o2[3];
-                    if (role == VVB200_ROLE_DRUDE) {
-                        scalePair<mixed>(vs, vq, fs, fq, Vn, sA, sC, sD, o1, o2);
-#pragma unroll
-                        for (int d = 0; d < 3; d++) { vs[d] = o1[d]; vq[d] = o2[d]; }
-                    } else {
-                        scalePair<mixed>(vq, vs, fq, fs, Vn, sA, sC, sD, o1, o2);
-#pragma unroll
-                        for (int d = 0; d < 3; d++) { vq[d] = o1[d]; vs[d] = o2[d]; }
-                    }
-                    writeVel = true;
-                }
-                if (cosine) { vs[0] += Vb * cphs; vq[0] += Vb * cq; }   // restorePeriodicVelocityBias
-            } else if (cosine) {
-                // non-thermostatted atoms still see remove then restore (cosineAccelerate.cu:63-84)
-                vs[0] -= Vb * cphs; vs[0] += Vb * cphs;
-                vq[0] -= Vb * cq; vq[0] += Vb * cq;
-                writeVel = true;
-            }
-
-            if (VARIANT == VAR_SCALE_ONLY) {
-                if (writeVel) {
-                    mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
-                    st_stream(velm + idx, o);
-                }
-                continue;
-            }
-            if (VARIANT == VAR_SCALE_DELTA) {
-                // integrateMiddlePos1 + Pos2 (middle.cu:33-41, 51-59): posDelta = oldDelta = dt/2 v0 + dt/2 v', for
-                // OpenMM's position constraints to work on before vvb200_middle_finish
-                if (writeVel) {
-                    mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
-                    st_stream(velm + idx, o);
-                }
-                if (ws != 0) {
-                    mixed4 d;
-                    d.x = halfdt * vs0[0]; d.x += halfdt * vs[0];
-                    d.y = halfdt * vs0[1]; d.y += halfdt * vs[1];
-                    d.z = halfdt * vs0[2]; d.z += halfdt * vs[2];
-                    d.w = 0;
-                    st_stream(reinterpret_cast<mixed4 *>(p.posDelta) + idx, d);
-                    st_stream(reinterpret_cast<mixed4 *>(p.oldDelta) + idx, d);
-                }
-                continue;
-            }
-
-            bool writePos = false;
-            if (VARIANT == VAR_VV_FIRST) {
-                // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
-                // particle and (redundantly) its partner
-                for (int who = 0; who < 2; who++) {
-                    if (who == 1 && role == VVB200_ROLE_NONE) break;
-                    const int js = who == 0 ? sl : psl;
-                    mixed *v = who == 0 ? vs : vq;
-                    const mixed w = who == 0 ? ws : wq;
-                    if (w == 0) continue;
-                    real ex = 0, ey = 0, ez = 0;
-                    if (EXTRA && p.extraForces) {
-                        const uint32_t mj = who == 0 ? mw : st.meta[js];
-                        if (p.hasLD && (mj & VVB200_META_LD)) {
-                            const real3 f = ldForce[p.ldSlot[t0 + js - sl0]];
-                            ex = f.x; ey = f.y; ez = f.z;
-                        }
-                        if (p.hasField) {
-                            const int cnt = (mj >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
-                            const real q = who == 0 ? pq.w : pqq.w;
-                            for (int c = 0; c < cnt; c++) ez += efscale * q;
-                        }
-                        if (cosine) {
-                            const double c = who == 0 ? cphs : cq;
-                            ex = (real) (ex + accel * c * vv_recip(w));
-                        }
-                    }
-                    const long long fx = st.f[0][Stage::FORCE ? js : 0], fy = st.f[1][Stage::FORCE ? js : 0],
-                                    fz = st.f[2][Stage::FORCE ? js : 0];
-                    v[0] += 0.5 * stepSize * w * ex + fscaleVV * w * fx;
-                    v[1] += 0.5 * stepSize * w * ey + fscaleVV * w * fy;
-                    v[2] += 0.5 * stepSize * w * ez + fscaleVV * w * fz;
-                }
-                // posDelta = dt*v ; x += posDelta ; v = posDelta/dt  (velocityVerlet.cu:25,52-58)
-                if (ws != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        ds[d] = stepSize * vs[d];
-                        xs[d] += ds[d];
-                        vs[d] = (mixed) (invStepSize * ds[d]);
-                    }
-                    writePos = writeVel = true;
-                }
-                if (role != VVB200_ROLE_NONE && wq != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        dq[d] = stepSize * vq[d];
-                        vq[d] = (mixed) (invStepSize * dq[d]);
-                    }
-                }
-            } else {
-                // middle scheme without constraints: posDelta = oldDelta = halfdt*v0 + halfdt*v', so
-                // integrateMiddlePos3 leaves v' unchanged and moves x by posDelta (middle.cu:33-98)
-                if (ws != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        ds[d] = halfdt * vs0[d];
-                        ds[d] += halfdt * vs[d];
-                        xs[d] += ds[d];
-                    }
-                    writePos = writeVel = true;
-                }
-                if (role != VVB200_ROLE_NONE && wq != 0) {
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        dq[d] = halfdt * vq0[d];
-                        dq[d] += halfdt * vq[d];
-                    }
-                }
-            }
-
-            // ---- Drude hard wall (middle.cu:114-220), evaluated by both members of the pair ----------
-            if (p.hardwall && role != VVB200_ROLE_NONE) {
-                // Pre-test in `real` arithmetic on the raw operands: the new separation is (posq_s - posq_q) +
-                // (corr_s - corr_q) + (ds - dq); the first difference is exact or off by < 4e-9 nm (neighbouring floats),
-                // so the squared distance is good to ~1e-6 relative and a 1e-4 margin is conservative.  Only a pair
-                // that might touch the wall pays for the partner's fp64 position and the reference's sqrt / reciprocal.
-                const real sx = (pq.x - pqq.x) + (cs.x - cqr.x) + (real) (ds[0] - dq[0]);
-                const real sy = (pq.y - pqq.y) + (cs.y - cqr.y) + (real) (ds[1] - dq[1]);
-                const real sz = (pq.z - pqq.z) + (cs.z - cqr.z) + (real) (ds[2] - dq[2]);
-                if (!(sx * sx + sy * sy + sz * sz < maxD2safe)) {
-                    mixed xq[3] = {pqq.x + (mixed) cqr.x, pqq.y + (mixed) cqr.y, pqq.z + (mixed) cqr.z};
-#pragma unroll
-                    for (int d = 0; d < 3; d++) xq[d] += dq[d];
-                    // the reference re-reads positions from posq (+ posqCorrection): apply the same rounding
-                    if (P::kMixed) {
-#pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            real hi, lo;
-                            if (ws != 0) { splitPos<MODE>(xs[d], hi, lo); xs[d] = hi + (mixed) lo; }
-                            if (wq != 0) { splitPos<MODE>(xq[d], hi, lo); xq[d] = hi + (mixed) lo; }
-                        }
-                    }
-                    const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
-                    mixed *pos1 = selfIsDrude ? xs : xq, *pos2 = selfIsDrude ? xq : xs;
-                    const mixed dx = pos1[0] - pos2[0], dy = pos1[1] - pos2[1], dz = pos1[2] - pos2[2];
-                    const mixed d2 = dx * dx + dy * dy + dz * dz;
-                    mixed *vel1 = selfIsDrude ? vs : vq, *vel2 = selfIsDrude ? vq : vs;
-                    const mixed w1 = selfIsDrude ? ws : wq, w2 = selfIsDrude ? wq : ws;
-                    const mixed r = vv_sqrt<MODE, mixed>(d2);
-                    const mixed rInv = vv_recip(r);
-                    if (rInv * maxD < 1) {
-                        const mixed bond[3] = {dx * rInv, dy * rInv, dz * rInv};
-                        const mixed mass1 = vv_recip(w1), mass2 = vv_recip(w2);
-                        const mixed deltaR = r - maxD;
-                        mixed deltaT = stepSize;
-                        mixed dotvr1 = vel1[0] * bond[0] + vel1[1] * bond[1] + vel1[2] * bond[2];
-                        mixed vp1[3];
-#pragma unroll
-                        for (int d = 0; d < 3; d++) vp1[d] = vel1[d] - bond[d] * dotvr1;
-                        if (w2 == 0) {
-                            if (dotvr1 != 0) deltaT = deltaR / fabs(dotvr1);
-                            if (deltaT > stepSize) deltaT = stepSize;
-                            dotvr1 = -dotvr1 * hwScale / (fabs(dotvr1) * vv_sqrt<MODE, mixed>(mass1));
-                            const mixed dr = -deltaR + deltaT * dotvr1;
-#pragma unroll
-                            for (int d = 0; d < 3; d++) {
-                                pos1[d] += bond[d] * dr;
-                                vel1[d] = vp1[d] + bond[d] * dotvr1;
-                            }
-                        } else {
-                            const mixed invTotalMass = vv_recip(mass1 + mass2);
-                            mixed dotvr2 = vel2[0] * bond[0] + vel2[1] * bond[1] + vel2[2] * bond[2];
-                            mixed vp2[3];
-#pragma unroll
-                            for (int d = 0; d < 3; d++) vp2[d] = vel2[d] - bond[d] * dotvr2;
-                            const mixed vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
-                            dotvr1 -= vbCMass;
-                            dotvr2 -= vbCMass;
-                            if (dotvr1 != dotvr2) deltaT = deltaR / fabs(dotvr1 - dotvr2);
-                            if (deltaT > stepSize) deltaT = stepSize;
-                            const mixed vBond = hwScale / vv_sqrt<MODE, mixed>(mass1);
-                            dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabs(dotvr1);
-                            dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabs(dotvr2);
-                            const mixed dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
-                            const mixed dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
-                            dotvr1 += vbCMass;
-                            dotvr2 += vbCMass;
-#pragma unroll
-                            for (int d = 0; d < 3; d++) {
-                                pos1[d] += bond[d] * dr1;
-                                pos2[d] += bond[d] * dr2;
-                                vel1[d] = vp1[d] + bond[d] * dotvr1;
-                                vel2[d] = vp2[d] + bond[d] * dotvr2;
-                            }
-                        }
-                        // the reference writes the touched members unconditionally (middle.cu:166-172, 204-219)
-                        if (selfIsDrude || w2 != 0) writePos = writeVel = true;
-                    }
-                }
-            }
-
-            if (writeVel) {
-                mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
-                st_stream(velm + idx, o);
-            }
-            if (POS && writePos) {
-                real4 o;
-                if (P::kMixed) {
-                    real4 oc;
-                    splitPos<MODE>(xs[0], o.x, oc.x);
-                    splitPos<MODE>(xs[1], o.y, oc.y);
-                    splitPos<MODE>(xs[2], o.z, oc.z);
-                    o.w = pq.w;
-                    oc.w = 0;
-                    st_stream(posq + idx, o);
-                    st_stream(corr + idx, oc);
-                } else {
-                    o.x = (real) xs[0]; o.y = (real) xs[1]; o.z = (real) xs[2]; o.w = pq.w;
-                    st_stream(posq + idx, o);
-                }
-            }
-        }
+        passBTile<MODE, VARIANT, EXTRA>(p, cx, st, tid);
         mbarArrive(empty + s);   // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
     }

@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs twice: through the single-launch resident kernel (the default for systems that fit in
+    shared memory, csrc/vvb200_resident.cuh) and through the two streaming passes (what large systems use)."""
+    if metafunc.definition.get_closest_marker("gpu") is not None:
+        if "step_path" not in metafunc.fixturenames:
+            metafunc.fixturenames.append("step_path")
+        metafunc.parametrize("step_path", ["resident", "streaming"], indirect=True)
+
+
+@pytest.fixture
+def step_path(request, monkeypatch):
+    monkeypatch.setenv("VVB200_RESIDENT", "1" if request.param == "resident" else "0")
+    return request.param
+
+
 @pytest.fixture(scope="session")
 def vv():
     """the product package (ctypes over libvvb200.so); builds the library if it is missing"""

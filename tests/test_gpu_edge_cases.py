@@ -156,7 +156,7 @@ def test_error_returns(vv):
     torch.cuda.synchronize()
 
 
-def test_viscosity_and_launch_count(vv, vo):
+def test_viscosity_and_launch_count(vv, vo, step_path):
     spec = vv.make_bulk_ionic_liquid(30)
     params = vv.Params(cos_acceleration=0.02).resolved_for(spec)
     host = vv.make_state(spec, "mixed")
@@ -165,6 +165,31 @@ def test_viscosity_and_launch_count(vv, vo):
     assert v0 == 0.0 and iv0 == 0.0                         # defined before the first step (the reference's is not)
     bufs = vv.DeviceBuffers(host)
     plan.step(bufs, steps=2, inv_box_z=1.0 / host.box[2])
-    assert plan.launch_count == 4                           # 2 launches per step, no host sync
+    # one launch per step when the system is resident in shared memory, else two; never a host sync
+    assert plan.launch_count == (2 if step_path == "resident" else 4)
+    assert plan.resident_launch_count == (2 if step_path == "resident" else 0)
     v, iv = plan.viscosity(host.box)
     assert v != 0.0 and np.isfinite(iv)
+
+
+def test_resident_kernel_several_tiles_per_block(vv, vo, step_path, monkeypatch):
+    """above 2 x 148 tiles the resident kernel keeps several tiles per block (one block per SM); not the default at
+    this size (the streaming passes are faster there) but it must stay correct: same results as the two passes"""
+    if step_path != "resident":
+        pytest.skip("resident-only case")
+    monkeypatch.setenv("VVB200_RESIDENT_MAX_PARTICLES", "400000")
+    spec = vv.make_bulk_ionic_liquid(4500)                  # 166,500 particles -> 326 tiles -> 3 tiles per block
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", force_sigma=1.0)
+    one, two = vv.Plan(spec, params, "mixed").upload(), vv.Plan(spec, params, "mixed").upload()
+    two.set_resident_mode(0)
+    a, b = vv.DeviceBuffers(host), vv.DeviceBuffers(host)
+    one.step(a, steps=3)
+    two.step(b, steps=3)
+    assert one.resident_launch_count == 3 and one.launch_count == 3
+    assert two.resident_launch_count == 0 and two.launch_count == 6
+    ha, hb = a.to_host(), b.to_host()
+    n = spec.n
+    assert rel_err(ha.velm[:n, :3], hb.velm[:n, :3]) <= 1e-10 and rel_err(ha.positions()[:n], hb.positions()[:n]) <= 1e-12
+    sa, sb = one.thermostat_state(), two.thermostat_state()
+    assert rel_err(sa["ke2"], sb["ke2"]) <= 1e-13 and rel_err(sa["vscale"], sb["vscale"]) <= 1e-13
