@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-config2", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="multi-GPU exchange of the 10-double reduction vector: NVLink peer memory inside the NHC kernel, or NCCL")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
@@ -220,6 +221,58 @@ def pinned_state(vv, host):
     return st
 
 
+def small_system_leg(vv, torch, precision, n_ip=1250, steps=400):
+    """BASELINE configs[1]: 1,250 ion pairs = 46,250 particles, TGNH, middle scheme, hard wall.  The whole step is ONE
+    launch (csrc/vvb200_resident.cuh); timed eagerly through the C ABI and replayed from a CUDA graph."""
+    spec = vv.make_bulk_ionic_liquid(n_ip)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, precision, force_sigma=FORCE_SIGMA)
+    plan = vv.Plan(spec, params, precision).upload()
+    b = vv.DeviceBuffers(host)
+    st = torch.cuda.current_stream()
+    for _ in range(10):
+        plan.step_middle(b)
+    torch.cuda.synchronize()
+    l0, r0 = plan.launch_count, plan.resident_launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        plan.step_middle(b)
+    e1.record(st)
+    torch.cuda.synchronize()
+    eager_us = 1e3 * e0.elapsed_time(e1) / steps
+    launches = (plan.launch_count - l0) / steps
+    resident = (plan.resident_launch_count - r0) / steps
+    graph_us = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(st)
+        with torch.cuda.stream(side):
+            plan.step_middle(b)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(20):
+                    plan.step_middle(b)
+            for _ in range(3):
+                g.replay()
+            side.synchronize()
+            e0.record(side)
+            for _ in range(steps // 20):
+                g.replay()
+            e1.record(side)
+            side.synchronize()
+        graph_us = 1e3 * e0.elapsed_time(e1) / (20 * (steps // 20))
+    except Exception as e:  # noqa: BLE001
+        graph_us = f"capture failed: {e}"
+    return {"workload": f"BASELINE configs[1]: Drude ionic-liquid bulk, {n_ip} ion pairs = {spec.n} particles, TGNH 3 groups, "
+                        f"middle scheme, hard wall, {precision}",
+            "us_per_step": eager_us, "cuda_graph_us_per_step": graph_us, "launches_per_step": launches,
+            "single_launch_resident_steps_per_step": resident,
+            "value": spec.n / (eager_us * 1e-6), "unit": UNIT,
+            "note": "latency-bound (1.5 MB of state): no roofline fraction; the reference's kernels need 10 launches + a "
+                    "blocking host round trip for the same step (profiles/configs_r01.json)"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -382,6 +435,12 @@ def main():
                        "launches_per_step": nl / ksteps, "speedup_device_resident": rms / ms_per_step}
             del ref, rb, oracle
 
+    # ---- BASELINE configs[1] (run-bulk.py-sized Drude bulk, ~50k particles): latency-bound, so microseconds and
+    #      launches per step instead of a roofline fraction; rank 0, single-GPU runs ---------------
+    config2 = None
+    if rank == 0 and world == 1 and not args.no_config2:
+        config2 = small_system_leg(vv, torch, args.precision)
+
     # ---- CPU baseline (rank 0, single-GPU runs only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -401,6 +460,7 @@ def main():
                                         "NCCL all-reduce of 10 doubles") if world > 1 else "none"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "reference_kernels_on_gpu": ref_gpu,
+                "config2_small_system": config2,
                 "clocks": clocks.summary(),
                 "integrator_only_ns_per_day": 86400.0 / (ms_per_step * 1e-3) * params.step_size * 1e-3,
                 "thermostat": {"ke2": [float(x) for x in st["ke2"]], "vscale": [float(x) for x in st["vscale"]]}}

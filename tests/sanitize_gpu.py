@@ -29,11 +29,16 @@ for spec, params, kw in cases:
             cos = kw2.pop("cos", False)
             par = dataclasses.replace(params.resolved_for(spec), use_middle_scheme=middle)
             host = vv.make_state(spec, mode, **kw2)
-            plan = vv.Plan(spec, par, mode).upload()
-            bufs = vv.DeviceBuffers(host, with_pos_delta=True)
-            plan.step(bufs, steps=2, inv_box_z=1.0 / host.box[2] if cos else 0.0)
-            if middle and not spec.langevin.size:
-                plan.middle_kick(bufs); plan.middle_delta(bufs, 0); plan.thermostat(bufs); plan.middle_delta(bufs, 1); plan.middle_finish(bufs)
-            torch.cuda.synchronize()
-            print("ok", spec.name, mode, "middle" if middle else "vv", "tiled" if plan.tiled else "general", flush=True)
+            for resident in (1, 0):          # single-launch resident kernel, then the two streaming passes
+                plan = vv.Plan(spec, par, mode).upload()
+                plan.set_resident_mode(resident)
+                bufs = vv.DeviceBuffers(host, with_pos_delta=True)
+                plan.step(bufs, steps=2, inv_box_z=1.0 / host.box[2] if cos else 0.0)
+                if middle and not spec.langevin.size:
+                    plan.middle_kick(bufs); plan.middle_delta(bufs, 0); plan.thermostat(bufs); plan.middle_delta(bufs, 1); plan.middle_finish(bufs)
+                    plan.middle_kick(bufs); plan.middle_thermostat_delta(bufs); plan.middle_finish(bufs)
+                torch.cuda.synchronize()
+                assert bool(torch.isfinite(bufs.velm).all()), "non-finite velocities"
+                print("ok", spec.name, mode, "middle" if middle else "vv", "tiled" if plan.tiled else "general",
+                      f"resident launches {plan.resident_launch_count}", flush=True)
 print("sanitize driver done")
