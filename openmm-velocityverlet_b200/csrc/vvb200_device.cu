@@ -131,6 +131,9 @@ struct KParams {
     int stagesA, stagesB;
     // single-launch resident kernel (vvb200_resident.cuh)
     int tilesPerBlock, doReduce;
+    // streaming kernels: the tile range of this launch (the whole system unless the host pipeline splits a step) and
+    // whether its sums are added to those already in nhc->red
+    int tileBegin, tileEnd, accumulateRed;
     unsigned int *gridGen;   // generation word of its grid barrier
 };
 
@@ -698,6 +701,9 @@ struct vvb200_device_state {
     void *hPosq = nullptr, *hCorr = nullptr, *hVelm = nullptr;
     long long *hForce = nullptr;
     size_t stagedN = 0;
+    // vvb200_step_host pipeline: copy-in / copy-out streams and per-chunk events
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    std::vector<cudaEvent_t> pipeEvents;
     std::vector<void *> allocations;
 };
 
@@ -734,6 +740,10 @@ void vvb200_device_free(vvb200_plan *plan) {
         cudaFree(ptr);
     for (cudaEvent_t e : d->profEvents)
         cudaEventDestroy(e);
+    for (cudaEvent_t e : d->pipeEvents)
+        cudaEventDestroy(e);
+    if (d->sIn) cudaStreamDestroy(d->sIn);
+    if (d->sOut) cudaStreamDestroy(d->sOut);
     for (void *m : d->peerMapped)
         cudaIpcCloseMemHandle(m);
     delete d;
@@ -907,6 +917,7 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     KParams k;
     memset(&k, 0, sizeof k);
     k.N = p->N; k.paddedN = p->paddedN; k.numTiles = d->numTiles;
+    k.tileBegin = 0; k.tileEnd = d->numTiles;
     k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
     k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
@@ -968,7 +979,7 @@ template <int MODE, int KICK, bool EXTRA>
 static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
     static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", MINBLOCKS_A);
     k.stagesA = cfg.stages;
-    const int grid = std::max(1, std::min(k.numTiles, numSM * cfg.perSM));
+    const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
     kick_reduce_kernel<MODE, KICK, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
     return cudaGetLastError();
 }
@@ -977,7 +988,7 @@ template <int MODE, int VARIANT, bool EXTRA>
 static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
     static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", MINBLOCKS_B);
     k.stagesB = cfg.stages;
-    const int grid = std::max(1, std::min(k.numTiles, numSM * cfg.perSM));
+    const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
     scale_drift_kernel<MODE, VARIANT, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
     return cudaGetLastError();
 }
@@ -1052,6 +1063,13 @@ static int launchResident(KParams k, int numSM, cudaStream_t st) {
         grid = (k.numTiles + T - 1) / T;
     }
     k.tilesPerBlock = T;
+    // Cooperative launch: the runtime places the whole grid or nothing, so two contexts stepping on different streams
+    // of one GPU can never hold half of each other's blocks while both wait at their grid barriers.
+    static const int coop = envInt("VVB200_COOP", 1);
+    if (coop) {
+        void *args[] = {&k};
+        return cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(CTHREADS), args, smem(T), st) == cudaSuccess ? 1 : -1;
+    }
     kernel<<<grid, CTHREADS, smem(T), st>>>(k);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -1817,6 +1835,94 @@ extern "C" int vvb200_set_resident_mode(vvb200_plan *p, int mode) {
 extern "C" int64_t vvb200_resident_launch_count(const vvb200_plan *p) { return p && p->dev ? p->dev->residentLaunches : 0; }
 
 // ---- host-buffer entry point ---------------------------------------------------------------------
+// One middle-scheme step of a large system with the transfers overlapped (PCIe is full duplex, and pass A only needs
+// velocities and forces):
+//   copy-in stream :  velm+force chunk 0..C-1 | posq+corr chunk 0..C-1
+//   compute stream :      pass A chunk 0..C-1 (sums accumulate; the last chunk advances the NH chains)
+//                                             |  pass B chunk c as soon as its positions are in
+//   copy-out stream:                          |     velm+posq+corr chunk c back as soon as pass B chunk c is done
+// Chunks are contiguous tile ranges, so no molecule or Drude pair is ever split.  Results equal the unsplit step up to
+// the association order of the group sums.
+static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, cudaStream_t st) {
+    vvb200_device_state *d = p->dev;
+    const int numTiles = d->numTiles;
+    const int C = std::max(1, std::min(std::min(envInt("VVB200_HOST_CHUNKS", 8), 64), numTiles));
+    const size_t P = p->paddedN;
+    const size_t ms = mixedSize(p->precision) * 4, rs = realSize(p->precision) * 4;
+    const bool mixedMode = p->precision == VVB200_MIXED;
+    if (!d->sIn) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->sIn, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->sOut, cudaStreamNonBlocking));
+    }
+    while (d->pipeEvents.size() < (size_t) 3 * C + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d->pipeEvents.push_back(e);
+    }
+    cudaEvent_t *evA = d->pipeEvents.data(), *evB = evA + C, *evC = evB + C, evStart = evC[C], evDone = evC[C + 1];
+    CUDA_TRY(cudaEventRecord(evStart, st));
+    CUDA_TRY(cudaStreamWaitEvent(d->sIn, evStart, 0));
+    CUDA_TRY(cudaStreamWaitEvent(d->sOut, evStart, 0));
+    auto tileLo = [&](int c) { return (int) ((long long) numTiles * c / C); };
+    auto partLo = [&](int c) { return c >= C ? P : (size_t) p->tileStart[tileLo(c)]; };   // the last chunk takes the padding
+    char *dVelm = (char *) d->hVelm, *dPosq = (char *) d->hPosq, *dCorr = (char *) d->hCorr;
+    vvb200_buffers db;
+    memset(&db, 0, sizeof db);
+    db.posq = d->hPosq;
+    db.posq_correction = mixedMode ? d->hCorr : nullptr;
+    db.velm = d->hVelm;
+    db.force = d->hForce;
+    const bool cosine = p->par.cos_acceleration != 0;
+    const bool extra = cosine || !p->particlesElectrolyte.empty();   // pass A then reads posq too
+    // ---- velocities + forces in, pass A chunk by chunk ----
+    for (int c = 0; c < C; c++) {
+        const size_t lo = partLo(c), n = partLo(c + 1) - lo;
+        CUDA_TRY(cudaMemcpyAsync(dVelm + lo * ms, (const char *) hb->velm + lo * ms, n * ms, cudaMemcpyHostToDevice, d->sIn));
+        for (int k = 0; k < 3; k++)
+            CUDA_TRY(cudaMemcpyAsync(d->hForce + k * P + lo, hb->force + k * P + lo, n * sizeof(long long), cudaMemcpyHostToDevice, d->sIn));
+        if (extra) {
+            CUDA_TRY(cudaMemcpyAsync(dPosq + lo * rs, (const char *) hb->posq + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
+            if (mixedMode)
+                CUDA_TRY(cudaMemcpyAsync(dCorr + lo * rs, (const char *) hb->posq_correction + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
+        }
+        CUDA_TRY(cudaEventRecord(evA[c], d->sIn));
+        CUDA_TRY(cudaStreamWaitEvent(st, evA[c], 0));
+        KParams k = makeParams(p, &db, a);
+        k.tileBegin = tileLo(c);
+        k.tileEnd = tileLo(c + 1);
+        k.accumulateRed = c > 0;
+        k.fuseNHC = hasNH(p) && c == C - 1;
+        CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, cosine, k, d->numSM, st)));
+        p->launches++;
+    }
+    // ---- positions in, pass B, results out ----
+    for (int c = 0; c < C; c++) {
+        const size_t lo = partLo(c), n = partLo(c + 1) - lo;
+        if (!extra) {
+            CUDA_TRY(cudaMemcpyAsync(dPosq + lo * rs, (const char *) hb->posq + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
+            if (mixedMode)
+                CUDA_TRY(cudaMemcpyAsync(dCorr + lo * rs, (const char *) hb->posq_correction + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
+            CUDA_TRY(cudaEventRecord(evB[c], d->sIn));
+            CUDA_TRY(cudaStreamWaitEvent(st, evB[c], 0));
+        }
+        KParams k = makeParams(p, &db, a);
+        k.tileBegin = tileLo(c);
+        k.tileEnd = tileLo(c + 1);
+        CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, cosine, k, d->numSM, st)));
+        p->launches++;
+        CUDA_TRY(cudaEventRecord(evC[c], st));
+        CUDA_TRY(cudaStreamWaitEvent(d->sOut, evC[c], 0));
+        CUDA_TRY(cudaMemcpyAsync((char *) hb->velm + lo * ms, dVelm + lo * ms, n * ms, cudaMemcpyDeviceToHost, d->sOut));
+        CUDA_TRY(cudaMemcpyAsync((char *) hb->posq + lo * rs, dPosq + lo * rs, n * rs, cudaMemcpyDeviceToHost, d->sOut));
+        if (mixedMode)
+            CUDA_TRY(cudaMemcpyAsync((char *) hb->posq_correction + lo * rs, dCorr + lo * rs, n * rs, cudaMemcpyDeviceToHost, d->sOut));
+    }
+    CUDA_TRY(cudaEventRecord(evDone, d->sOut));
+    CUDA_TRY(cudaStreamWaitEvent(st, evDone, 0));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VVB200_OK;
+}
+
 extern "C" int vvb200_step_host(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, int steps, void *stream) {
     if (!p || !hb || steps < 0) {
         vvb200_set_error("vvb200_step_host: invalid argument");
@@ -1842,6 +1948,10 @@ extern "C" int vvb200_step_host(vvb200_plan *p, const vvb200_buffers *hb, const 
         d->stagedN = P;
     }
     const bool mixedMode = p->precision == VVB200_MIXED;
+    // one step of a large tiled system: overlap copy-in, the two passes and copy-out (VVB200_HOST_PIPELINE=0 disables)
+    if (steps == 1 && p->tiled && p->par.use_middle_scheme && p->imagePairs.empty() &&
+        p->N >= envInt("VVB200_HOST_PIPELINE_MIN", 1000000) && envInt("VVB200_HOST_PIPELINE", 1))
+        return stepHostPipelined(p, hb, a, st);
     CUDA_TRY(cudaMemcpyAsync(d->hVelm, hb->velm, P * 4 * ms, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->hForce, hb->force, P * 3 * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->hPosq, hb->posq, P * 4 * rs, cudaMemcpyHostToDevice, st));

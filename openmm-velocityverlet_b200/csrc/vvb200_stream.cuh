@@ -415,6 +415,7 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
         double v = 0;
         if (tid < NR)
             for (int w = 0; w < CTHREADS / 32; w++) v += sm.red[w][tid];
+        if (p.accumulateRed) v += work->red[tid];   // a step split into several launches over tile ranges (host pipeline)
         work->red[tid] = v;
         sm.red[0][tid] = v;      // thread `tid` is the only reader of column `tid`
     }
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
             return;
         int s = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
             const int4 d0 = __ldg(p.tileDesc + 2 * tile), d1 = __ldg(p.tileDesc + 2 * tile + 1);
             mbarWait(empty + s, phase ^ 1);
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
 
     int s = 0, buf = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+    for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
         PublishedA<MODE, EXTRA> &pub = sm.pub[buf];
@@ -966,7 +967,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
         const mixed *comCbar = reinterpret_cast<const mixed *>(p.comCbar);
         int s = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
             const int4 d0 = __ldg(p.tileDesc + 2 * tile), d1 = __ldg(p.tileDesc + 2 * tile + 1);
             mbarWait(empty + s, phase ^ 1);
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
@@ -1016,7 +1017,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     const BCtx<MODE> cx = makeBCtx<MODE>(p, EXTRA);
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+    for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
         passBTile<MODE, VARIANT, EXTRA>(p, cx, st, tid);

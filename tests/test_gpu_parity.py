@@ -231,6 +231,37 @@ def test_step_host_roundtrip(vv, vo):
     assert np.array_equal(got.velm, want.velm) and np.array_equal(got.posq, want.posq) and np.array_equal(got.corr, want.corr)
 
 
+@pytest.mark.parametrize("cos", [False, True])
+@pytest.mark.parametrize("precision", ["mixed", "single"])
+def test_step_host_pipelined(vv, vo, monkeypatch, cos, precision):
+    """one step through host buffers with copy-in / pass A / pass B / copy-out overlapped chunk by chunk (what
+    vvb200_step_host does for >= 1M particles; forced here at 15k with 5 chunks) equals the device-resident step up to
+    the association order of the group sums"""
+    monkeypatch.setenv("VVB200_HOST_PIPELINE_MIN", "1000")
+    monkeypatch.setenv("VVB200_HOST_CHUNKS", "5")
+    monkeypatch.setenv("VVB200_SMALL_TILES", "0")
+    spec = vv.make_bulk_ionic_liquid(400)
+    params = vv.Params(max_drude_distance=0.02, cos_acceleration=0.02 if cos else 0.0).resolved_for(spec)
+    host = vv.make_state(spec, precision)
+    inv_box_z = 1.0 / host.box[2] if cos else 0.0
+    p1, p2 = vv.Plan(spec, params, precision).upload(), vv.Plan(spec, params, precision).upload()
+    p1.set_resident_mode(0)
+    bufs = vv.DeviceBuffers(host)
+    got = host.copy()
+    for _ in range(3):                        # three single-step calls: state round-trips through the host every step
+        p1.step(bufs, steps=1, inv_box_z=inv_box_z)
+        p2.step_host(got, steps=1, inv_box_z=inv_box_z)
+    want = bufs.to_host()
+    assert p2.launch_count == 3 * 10          # 5 tile ranges x (pass A + pass B) per step
+    n = spec.n
+    tol = 1e-11 if precision == "mixed" else 2e-5
+    err = rel_err if precision == "mixed" else rms_err
+    assert err(got.velm[:n, :3], want.velm[:n, :3]) <= tol and err(got.positions()[:n], want.positions()[:n]) <= tol
+    assert np.array_equal(got.velm[n:], want.velm[n:]) and np.array_equal(got.posq[n:], want.posq[n:])   # padding untouched
+    a, b = p1.thermostat_state(), p2.thermostat_state()
+    assert rel_err(b["ke2"], a["ke2"]) <= (1e-12 if precision == "mixed" else 1e-5)
+
+
 def test_large_system_properties(vv, vo):
     """>=1M particles (beyond what the scalar oracle checks every element of in seconds): size-independent
     properties -- group orthogonality: after a thermostat application with factors
