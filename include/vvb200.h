@@ -249,6 +249,32 @@ int vvb200_get_com_velocities(vvb200_plan *plan, void *host_out, void *stream);
 /* kernel launches issued by this plan since creation (bench.py's gpu_launches) */
 int64_t vvb200_launch_count(const vvb200_plan *plan);
 
+/* ---- checkpoint ------------------------------------------------------------------
+ * What Integrator::createCheckpoint / loadCheckpoint need from this path: the Nose-Hoover chain
+ * state (the reference keeps eta / eta_dot / eta_dotdot as VVIntegrator members and LOSES them on
+ * resume: a restarted run re-equilibrates its thermostat), the last scale factors and velocity
+ * bias, and whether the VV scheme's extra forces are valid.  A flat little-endian blob with a
+ * magic/version header; load refuses blobs written for another group count or chain length. */
+int vvb200_checkpoint_size(const vvb200_plan *plan, int64_t *bytes);
+int vvb200_checkpoint_save(vvb200_plan *plan, void *host_out, int64_t capacity, void *stream);
+int vvb200_checkpoint_load(vvb200_plan *plan, const void *host_in, int64_t bytes, void *stream);
+
+/* ---- group temperatures on demand ------------------------------------------------
+ * Temperatures of the atom / molecular-COM / Drude groups of the CURRENT velocities, without
+ * stepping and without touching the thermostat state: one reduction launch and an 80-byte read
+ * back.  Replaces the host path of examples/ommhelper/reporter/drudetemperaturereporter.py:98-129
+ * (download of N velocities + numpy) with the thermostat's own definitions
+ * (drudeNoseHoover.cu:55-114, DOFs of CudaVVKernels.cpp:516-573).  ke2 = sum m v^2 per group
+ * (kJ/mol), temperature = ke2 / (dof kB).  Must not be called between vvb200_middle_kick_reduce
+ * and vvb200_middle_nhc_scale_drift (it reuses the reduction vector).  Synchronises the stream. */
+typedef struct {
+    int32_t num_temp_groups;
+    double ke2[3], dof[3], temperature[3];
+    double velocity_bias;    /* cosine runs: amplitude of the velocity profile, removed before the sums */
+} vvb200_temperatures;
+int vvb200_measure_temperatures(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args,
+                                vvb200_temperatures *out, void *stream);
+
 /* Small systems (all tiles co-resident in shared memory, up to ~227k particles in mixed mode) run
  * the whole thermostatted step -- what CudaVVKernels.cpp:144-185 + 670-754 do in 9-10 launches and
  * a blocking host round trip -- as ONE launch with a grid barrier (csrc/vvb200_resident.cuh).

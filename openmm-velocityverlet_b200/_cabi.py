@@ -65,6 +65,11 @@ class _ThermostatState(C.Structure):
                 ("eta_dot", C.c_double * (3 * (MAX_CHAINS + 1))), ("eta_dotdot", C.c_double * (3 * MAX_CHAINS))]
 
 
+class _Temperatures(C.Structure):
+    _fields_ = [("num_temp_groups", C.c_int32), ("ke2", C.c_double * 3), ("dof", C.c_double * 3),
+                ("temperature", C.c_double * 3), ("velocity_bias", C.c_double)]
+
+
 @dataclass
 class Params:
     """VVIntegrator's parameters (VVIntegrator.h:62-431); defaults are the constructor's
@@ -156,6 +161,10 @@ def load_library(path=None):
     lib.vvb200_launch_count.argtypes = [vp]
     lib.vvb200_launch_count.restype = i64
     lib.vvb200_step_host.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, vp]
+    lib.vvb200_checkpoint_size.argtypes = [vp, P(i64)]
+    lib.vvb200_checkpoint_save.argtypes = [vp, vp, i64, vp]
+    lib.vvb200_checkpoint_load.argtypes = [vp, vp, i64, vp]
+    lib.vvb200_measure_temperatures.argtypes = [vp, P(_Buffers), P(_StepArgs), P(_Temperatures), vp]
     lib.vvb200_set_resident_mode.argtypes = [vp, C.c_int]
     lib.vvb200_resident_launch_count.argtypes = [vp]
     lib.vvb200_resident_launch_count.restype = i64
@@ -389,6 +398,28 @@ class Plan:
             for i, v in enumerate(flat):
                 dst[i] = v
         _check(self.lib, self.lib.vvb200_set_thermostat_state(self.h, C.byref(s), self._stream(stream)))
+
+    def checkpoint_save(self, stream=None):
+        """the integrator's part of a checkpoint (NH chain state, last scale factors, VV extra-force flag) as bytes"""
+        n = C.c_int64()
+        _check(self.lib, self.lib.vvb200_checkpoint_size(self.h, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        _check(self.lib, self.lib.vvb200_checkpoint_save(self.h, _ptr(buf), n.value, self._stream(stream)))
+        return buf.tobytes()
+
+    def checkpoint_load(self, blob, stream=None):
+        buf = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
+        _check(self.lib, self.lib.vvb200_checkpoint_load(self.h, _ptr(buf), buf.size, self._stream(stream)))
+
+    def measure_temperatures(self, bufs, inv_box_z=0.0, stream=None):
+        """group temperatures of the current velocities, no stepping (the Drude-temperature reporter's numbers)"""
+        b = bufs.c_struct()
+        a = _StepArgs(0, inv_box_z)
+        t = _Temperatures()
+        _check(self.lib, self.lib.vvb200_measure_temperatures(self.h, C.byref(b), C.byref(a), C.byref(t), self._stream(stream)))
+        ng = t.num_temp_groups
+        return {"num_temp_groups": ng, "ke2": np.array(t.ke2[:ng]), "dof": np.array(t.dof[:ng]),
+                "temperature": np.array(t.temperature[:ng]), "velocity_bias": t.velocity_bias}
 
     def viscosity(self, box, stream=None):
         v, iv = C.c_double(), C.c_double()

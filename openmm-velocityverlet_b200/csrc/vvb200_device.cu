@@ -1817,6 +1817,116 @@ extern "C" int vvb200_get_com_velocities(vvb200_plan *p, void *hostOut, void *st
     return VVB200_OK;
 }
 
+// ---- checkpoint ---------------------------------------------------------------------------------
+struct CheckpointBlob {
+    uint32_t magic, version;
+    int32_t numTG, nc, extraForcesValid, reserved;
+    vvb200_thermostat_state state;
+};
+static const uint32_t kCheckpointMagic = 0x32425656u;   // "VVB2"
+
+extern "C" int vvb200_checkpoint_size(const vvb200_plan *p, int64_t *bytes) {
+    if (!p || !bytes) {
+        vvb200_set_error("vvb200_checkpoint_size: null argument");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    *bytes = (int64_t) sizeof(CheckpointBlob);
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_checkpoint_save(vvb200_plan *p, void *out, int64_t capacity, void *stream) {
+    if (!p || !p->dev || !out) {
+        vvb200_set_error("vvb200_checkpoint_save: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    if (capacity < (int64_t) sizeof(CheckpointBlob)) {
+        vvb200_set_error("vvb200_checkpoint_save: buffer of %lld bytes, %zu needed", (long long) capacity, sizeof(CheckpointBlob));
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    CheckpointBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = kCheckpointMagic;
+    b.version = 1;
+    b.numTG = p->numTempGroup;
+    b.nc = p->par.num_nh_chains;
+    b.extraForcesValid = p->dev->extraForcesValid ? 1 : 0;
+    int rc = vvb200_get_thermostat_state(p, &b.state, stream);
+    if (rc) return rc;
+    memcpy(out, &b, sizeof b);
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_checkpoint_load(vvb200_plan *p, const void *in, int64_t bytes, void *stream) {
+    if (!p || !p->dev || !in) {
+        vvb200_set_error("vvb200_checkpoint_load: plan not uploaded or null argument");
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    CheckpointBlob b;
+    if (bytes < (int64_t) sizeof b) {
+        vvb200_set_error("vvb200_checkpoint_load: truncated checkpoint (%lld of %zu bytes)", (long long) bytes, sizeof b);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    memcpy(&b, in, sizeof b);
+    if (b.magic != kCheckpointMagic || b.version != 1) {
+        vvb200_set_error("vvb200_checkpoint_load: not a vvb200 checkpoint (magic %08x version %u)", b.magic, b.version);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if (b.numTG != p->numTempGroup || b.nc != p->par.num_nh_chains) {
+        vvb200_set_error("vvb200_checkpoint_load: checkpoint has %d temperature groups x %d chains, this integrator %d x %d",
+                         b.numTG, b.nc, p->numTempGroup, p->par.num_nh_chains);
+        return VVB200_ERR_CONFLICT;
+    }
+    int rc = vvb200_set_thermostat_state(p, &b.state, stream);
+    if (rc) return rc;
+    // scale factors, energies and bias of the last step (what getViscosity / the temperature getters report)
+    cudaStream_t st = (cudaStream_t) stream;
+    NhcDevice *n = p->dev->nhc;
+    CUDA_TRY(cudaMemcpyAsync(n->ke2, b.state.ke2, sizeof n->ke2, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(n->vscale, b.state.vscale, sizeof n->vscale, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(&n->vBias, &b.state.velocity_bias, sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->dev->extraForcesValid = b.extraForcesValid != 0;
+    return VVB200_OK;
+}
+
+// ---- group temperatures of the current velocities (reporter path) ----------------------------------------
+extern "C" int vvb200_measure_temperatures(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a,
+                                           vvb200_temperatures *out, void *stream) {
+    int rc = checkStepArgs(p, b, "vvb200_measure_temperatures", false, false);
+    if (rc) return rc;
+    if (!out) {
+        vvb200_set_error("vvb200_measure_temperatures: null output");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    memset(out, 0, sizeof *out);
+    out->num_temp_groups = p->numTempGroup;
+    for (int g = 0; g < 3; g++) out->dof[g] = p->dofGlobal[g];
+    if (!hasNH(p))
+        return VVB200_OK;
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool cosine = p->par.cos_acceleration != 0;
+    if (p->tiled) {
+        KParams k = makeParams(p, b, a);
+        k.fuseNHC = 0;                   // sums only: the chains and scale factors stay as they are
+        CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
+        p->launches++;
+    } else if ((rc = generalThermostat(p, b, a, true, false, false, st))) {
+        return rc;
+    }
+    double red[VVB200_NRED];
+    CUDA_TRY(cudaMemcpyAsync(red, p->dev->nhc->red, sizeof red, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const double V = cosine ? red[3] * (1.0 / p->totalMassGlobal) : 0.0;   // nhcFinish's expression
+    out->velocity_bias = V;
+    for (int g = 0; g < p->numTempGroup; g++) {
+        double ke2 = red[g];
+        if (cosine) ke2 = red[g] - 2.0 * V * red[4 + g] + V * V * red[7 + g];
+        out->ke2[g] = ke2;
+        out->temperature[g] = out->dof[g] > 0 ? ke2 / (out->dof[g] * BOLTZ_D) : 0.0;
+    }
+    return VVB200_OK;
+}
+
 #ifdef VVB200_TRACE
 extern "C" int vvb200_debug_trace(unsigned long long *out, int n) {
     return (int) cudaMemcpyFromSymbol(out, g_vvb200Trace, sizeof(unsigned long long) * n);

@@ -199,6 +199,14 @@ class VVIntegrator:
         inv_box_z = 1.0 / ctx.box[2] if self._cosAcceleration != 0 else 0.0
         self._randomIndex = self._plan.step(ctx.buffers, steps=int(steps), random_index=self._randomIndex, inv_box_z=inv_box_z)
 
+    def getGroupTemperatures(self):
+        """{"temperature": [T_atom, T_COM, T_Drude][:numGroups], "ke2", "dof"} of the current velocities, measured on the
+        device (what examples/ommhelper/reporter/drudetemperaturereporter.py:98-129 computes on the host with numpy)"""
+        ctx = self._context
+        ctx._require_device()
+        inv_box_z = 1.0 / ctx.box[2] if self._cosAcceleration != 0 else 0.0
+        return self._plan.measure_temperatures(ctx.buffers, inv_box_z=inv_box_z)
+
     def getViscosity(self):
         """[vMax, 1/viscosity] (VVIntegrator.cpp:378-383)"""
         v, inv = self._plan.viscosity(self._context.box)
@@ -225,6 +233,30 @@ class Context:
 
     def getState(self):
         return self.buffers.to_host()
+
+    # ---- OpenMM's Context.createCheckpoint / loadCheckpoint: positions, velocities, box AND the integrator's own state
+    #      (Integrator::createCheckpoint hook; the reference does not implement it and restarts its NH chains cold) ----
+    def createCheckpoint(self):
+        import io
+        st = self.getState()
+        out = io.BytesIO()
+        np.savez(out, posq=st.posq, corr=st.corr if st.corr is not None else np.zeros(0), velm=st.velm,
+                 box=np.array(self.box), random_index=np.array([self.integrator._randomIndex]),
+                 integrator=np.frombuffer(self.integrator._plan.checkpoint_save(), dtype=np.uint8))
+        return out.getvalue()
+
+    def loadCheckpoint(self, blob):
+        import io
+        import torch
+        self._require_device()
+        z = np.load(io.BytesIO(blob))
+        self.buffers.posq.copy_(torch.from_numpy(z["posq"]))
+        if self.buffers.corr is not None:
+            self.buffers.corr.copy_(torch.from_numpy(z["corr"]))
+        self.buffers.velm.copy_(torch.from_numpy(z["velm"]))
+        self.box = tuple(float(x) for x in z["box"])
+        self.integrator._randomIndex = int(z["random_index"][0])
+        self.integrator._plan.checkpoint_load(z["integrator"].tobytes())
 
     def _require_device(self):
         if self.buffers is None:

@@ -193,3 +193,96 @@ def test_resident_kernel_several_tiles_per_block(vv, vo, step_path, monkeypatch)
     assert rel_err(ha.velm[:n, :3], hb.velm[:n, :3]) <= 1e-10 and rel_err(ha.positions()[:n], hb.positions()[:n]) <= 1e-12
     sa, sb = one.thermostat_state(), two.thermostat_state()
     assert rel_err(sa["ke2"], sb["ke2"]) <= 1e-13 and rel_err(sa["vscale"], sb["vscale"]) <= 1e-13
+
+
+def _reporter_temperatures(spec, velm, use_cmm):
+    """independent numpy statement of what the reference's Drude-temperature reporter prints
+    (examples/ommhelper/reporter/drudetemperaturereporter.py:98-129): COM / atom / Drude kinetic energies x2 and DOFs"""
+    kB = 1.380649e-23 * 6.02214076e23 / 1000.0
+    n = spec.n
+    v = velm[:n, :3].astype(np.float64).copy()
+    m = spec.masses.astype(np.float64).copy()
+    mol = spec.mol_id
+    mass_mol = np.bincount(mol, weights=m, minlength=spec.n_mol)
+    vmol = np.stack([np.bincount(mol, weights=m * v[:, d], minlength=spec.n_mol) for d in range(3)], axis=1)
+    vmol = vmol / np.where(mass_mol > 0, mass_mol, 1.0)[:, None]
+    ke2_com = float(np.sum(mass_mol * np.sum(vmol ** 2, axis=1)))
+    dof_com = 3 * np.count_nonzero(mass_mol) - (3 if use_cmm else 0)
+    nd = spec.drude_pairs.shape[0]
+    dof_atom = 3 * np.count_nonzero(m) - 3 * np.count_nonzero(mass_mol) - spec.constraints.shape[0] - 3 * nd
+    v -= vmol[mol]
+    is_drude = np.zeros(n, bool)
+    for d, c in spec.drude_pairs:
+        md, mc = m[d], m[c]
+        vd, vc = v[d].copy(), v[c].copy()
+        v[d], v[c] = vd - vc, (md * vd + mc * vc) / (md + mc)
+        m[d], m[c] = md * mc / (md + mc), md + mc
+        is_drude[d] = True
+    mvv = m * np.sum(v ** 2, axis=1)
+    ke2_atom, ke2_drude = float(mvv[~is_drude].sum()), float(mvv[is_drude].sum())
+    return (np.array([ke2_atom, ke2_com, ke2_drude]), np.array([dof_atom, dof_com, 3 * nd]),
+            np.array([ke2_atom / (dof_atom * kB), ke2_com / (dof_com * kB), ke2_drude / (3 * nd * kB)]))
+
+
+@pytest.mark.parametrize("general", [False, True])
+def test_measure_temperatures_matches_the_reporter(vv, vo, general, monkeypatch):
+    """vvb200_measure_temperatures: one reduction launch, no stepping, thermostat state untouched; the numbers are the
+    reference reporter's (all particles thermostatted => same energies and DOFs)"""
+    if general:
+        monkeypatch.setenv("VVB200_FORCE_GENERAL", "1")
+    spec = vv.make_bulk_ionic_liquid(200, has_cmm=True)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", force_sigma=1.0)       # gentle frozen forces: two steps barely heat the box
+    plan = vv.Plan(spec, params, "mixed").upload()
+    assert plan.tiled != general
+    bufs = vv.DeviceBuffers(host)
+    plan.step(bufs, steps=2)
+    before = plan.thermostat_state()
+    state = bufs.to_host()
+    t = plan.measure_temperatures(bufs)
+    after = plan.thermostat_state()
+    for k in ("eta", "eta_dot", "eta_dotdot", "vscale", "ke2"):
+        assert np.array_equal(before[k], after[k]), k                  # measuring is not stepping
+    assert np.array_equal(bufs.to_host().velm, state.velm)
+    ke2, dof, temp = _reporter_temperatures(spec, state.velm, use_cmm=True)
+    assert t["num_temp_groups"] == 3
+    assert rel_err(t["dof"], dof) <= 1e-13      # the reference accumulates fractional per-particle DOFs in fp64 (13200.000000000036)
+    assert rel_err(t["ke2"], ke2) <= 1e-11 and rel_err(t["temperature"], temp) <= 1e-11
+    assert 150 < t["temperature"][0] < 600 and t["temperature"][2] < 50      # sane: ~333 K atoms, cold Drudes
+
+
+def test_checkpoint_resumes_bitwise(vv, vo):
+    """save after 3 steps, keep going 4 more; a fresh plan + loaded checkpoint + the saved arrays reproduces them bitwise
+    (the reference restarts its NH chains from zero on resume)"""
+    spec = vv.make_bulk_ionic_liquid(150)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed")
+    p1 = vv.Plan(spec, params, "mixed").upload()
+    b1 = vv.DeviceBuffers(host)
+    p1.step(b1, steps=3)
+    blob, saved = p1.checkpoint_save(), b1.to_host()
+    p1.step(b1, steps=4)
+    want, want_state = b1.to_host(), p1.thermostat_state()
+
+    p2 = vv.Plan(spec, params, "mixed").upload()
+    p2.checkpoint_load(blob)
+    b2 = vv.DeviceBuffers(saved)
+    p2.step(b2, steps=4)
+    got, got_state = b2.to_host(), p2.thermostat_state()
+    assert np.array_equal(got.velm, want.velm) and np.array_equal(got.posq, want.posq) and np.array_equal(got.corr, want.corr)
+    for k in ("eta", "eta_dot", "eta_dotdot", "vscale", "ke2"):
+        assert np.array_equal(got_state[k], want_state[k]), k
+    # without the checkpoint the chains restart cold and the trajectory differs
+    p3 = vv.Plan(spec, params, "mixed").upload()
+    b3 = vv.DeviceBuffers(saved)
+    p3.step(b3, steps=4)
+    assert not np.array_equal(b3.to_host().velm, want.velm)
+    # refused: truncated blob, foreign bytes, another chain length
+    with pytest.raises(vv.VVB200Error):
+        p2.checkpoint_load(blob[:40])
+    with pytest.raises(vv.VVB200Error):
+        p2.checkpoint_load(bytes(len(blob)))
+    other = vv.Plan(spec, dataclasses.replace(params, num_nh_chains=5), "mixed").upload()
+    with pytest.raises(vv.VVB200Error) as e:
+        other.checkpoint_load(blob)
+    assert e.value.code == 2

@@ -110,3 +110,24 @@ def test_context_steps_like_run_bulk(vv, vo):
     it.setStepSize(0.002)                       # picked up at the next step, like the reference
     it.step(1)
     assert np.isfinite(ctx.getState().velm).all()
+
+
+@pytest.mark.gpu
+def test_context_checkpoint_and_group_temperatures(vv, vo):
+    """Context.createCheckpoint / loadCheckpoint carry the integrator's NH-chain state (the reference drops it), and
+    getGroupTemperatures reports the three group temperatures from the device"""
+    spec, system = bulk_system(vv, 60)
+    it = vv.VVIntegrator(333.0, 10.0, 1.0, 40.0, 0.001)
+    it.setMaxDrudeDistance(0.02)
+    ctx = vv.Context(system, it, precision="mixed")
+    ctx.setState(vv.make_state(spec, "mixed"))
+    it.step(3)
+    blob = ctx.createCheckpoint()
+    it.step(2)
+    want = ctx.getState()
+    ctx.loadCheckpoint(blob)
+    it.step(2)
+    got = ctx.getState()
+    assert np.array_equal(got.velm, want.velm) and np.array_equal(got.posq, want.posq) and np.array_equal(got.corr, want.corr)
+    t = it.getGroupTemperatures()
+    assert t["num_temp_groups"] == 3 and np.all(t["temperature"] > 0) and np.all(t["dof"] > 0)
