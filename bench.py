@@ -381,20 +381,8 @@ def main():
             def e2e_step():
                 plan.step_host(pst, steps=1)           # vvb200_step_host: H2D + step + D2H, synchronises
         else:
-            tp = {k: torch.from_numpy(getattr(pst, k)) for k in ("posq", "corr", "velm", "force") if getattr(pst, k) is not None}
-
             def e2e_step():
-                bufs.posq.copy_(tp["posq"], non_blocking=True)
-                if bufs.corr is not None:
-                    bufs.corr.copy_(tp["corr"], non_blocking=True)
-                bufs.velm.copy_(tp["velm"], non_blocking=True)
-                bufs.force.copy_(tp["force"], non_blocking=True)
-                one_step()
-                tp["posq"].copy_(bufs.posq, non_blocking=True)
-                if bufs.corr is not None:
-                    tp["corr"].copy_(bufs.corr, non_blocking=True)
-                tp["velm"].copy_(bufs.velm, non_blocking=True)
-                torch.cuda.synchronize()
+                dplan.step_host(pst)                   # vvb200_step_host_begin | exchange of 10 doubles | _finish; synchronises
         for _ in range(3):
             e2e_step()
         barrier()
@@ -410,7 +398,7 @@ def main():
         e2e = {"value": n_global * ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": ke, "ms_per_step": 1e3 * dt / ke,
                "api": "vvb200_step_host (pinned host buffers)" if world == 1 else
-                      "Plan.middle_kick_reduce + NCCL all-reduce + Plan.middle_nhc_scale_drift with pinned H2D/D2H"}
+                      "vvb200_step_host_begin + exchange of the reduction vector + vvb200_step_host_finish (pinned host buffers)"}
 
     # ---- the reference's own CUDA kernels on this GPU (rank 0, single-GPU runs; reported, not the headline) ------
     ref_gpu = None

@@ -296,6 +296,14 @@ int vvb200_profile_read(vvb200_plan *plan, double *ms_pass_a, double *ms_pass_b,
  * Device staging buffers are owned by the plan. Synchronises. */
 int vvb200_step_host(vvb200_plan *plan, const vvb200_buffers *host_buf, const vvb200_step_args *args,
                      int steps, void *stream);
+/* For one step of a large system (>= 1M particles) vvb200_step_host overlaps the transfers with the two
+ * passes chunk by chunk (copy-in, compute and copy-out streams; PCIe is full duplex).  Molecule-
+ * partitioned multi-GPU runs use the same pipeline in two calls around their exchange of the
+ * reduction vector: _begin queues all copies in and runs pass A (returns without synchronising);
+ * the caller all-reduces vvb200_partials_ptr() unless the peer exchange is attached; _finish
+ * advances the NH chains, runs pass B, copies the results out and synchronises. */
+int vvb200_step_host_begin(vvb200_plan *plan, const vvb200_buffers *host_buf, const vvb200_step_args *args, void *stream);
+int vvb200_step_host_finish(vvb200_plan *plan, const vvb200_buffers *host_buf, const vvb200_step_args *args, void *stream);
 
 #ifdef __cplusplus
 }

@@ -161,6 +161,8 @@ def load_library(path=None):
     lib.vvb200_launch_count.argtypes = [vp]
     lib.vvb200_launch_count.restype = i64
     lib.vvb200_step_host.argtypes = [vp, P(_Buffers), P(_StepArgs), C.c_int, vp]
+    lib.vvb200_step_host_begin.argtypes = [vp, P(_Buffers), P(_StepArgs), vp]
+    lib.vvb200_step_host_finish.argtypes = [vp, P(_Buffers), P(_StepArgs), vp]
     lib.vvb200_checkpoint_size.argtypes = [vp, P(i64)]
     lib.vvb200_checkpoint_save.argtypes = [vp, vp, i64, vp]
     lib.vvb200_checkpoint_load.argtypes = [vp, vp, i64, vp]
@@ -441,6 +443,20 @@ class Plan:
         a, b, n = C.c_double(), C.c_double(), C.c_int32()
         _check(self.lib, self.lib.vvb200_profile_read(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def _host_buffers(self, host_state):
+        return _Buffers(_ptr(host_state.posq), _ptr(host_state.corr) if host_state.corr is not None else None,
+                        _ptr(host_state.velm), _ptr(host_state.force), None, None)
+
+    def step_host_begin(self, host_state, inv_box_z=0.0, stream=None):
+        """first half of a pipelined host-buffer step: all copies in are queued, pass A runs; does not synchronise"""
+        b, a = self._host_buffers(host_state), _StepArgs(0, inv_box_z)
+        _check(self.lib, self.lib.vvb200_step_host_begin(self.h, C.byref(b), C.byref(a), self._stream(stream)))
+
+    def step_host_finish(self, host_state, inv_box_z=0.0, stream=None):
+        """second half: NH chains (+ peer exchange), pass B, copies out; synchronises"""
+        b, a = self._host_buffers(host_state), _StepArgs(0, inv_box_z)
+        _check(self.lib, self.lib.vvb200_step_host_finish(self.h, C.byref(b), C.byref(a), self._stream(stream)))
 
     def step_host(self, host_state, steps=1, inv_box_z=0.0, stream=None):
         """vvb200_step_host: host arrays in, host arrays out (H2D + steps + D2H inside)."""

@@ -1953,7 +1953,10 @@ extern "C" int64_t vvb200_resident_launch_count(const vvb200_plan *p) { return p
 //   copy-out stream:                          |     velm+posq+corr chunk c back as soon as pass B chunk c is done
 // Chunks are contiguous tile ranges, so no molecule or Drude pair is ever split.  Results equal the unsplit step up to
 // the association order of the group sums.
-static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, cudaStream_t st) {
+// phase: 0 = the whole step (single GPU); 1 = everything up to the group sums (copy-in of all arrays is queued, pass A
+// runs chunk by chunk, the NH chains are NOT advanced); 2 = NH chains (with the peer exchange when attached), pass B
+// and copy-out.  Multi-GPU callers run 1, all-reduce the reduction vector if they use NCCL, then 2.
+static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, cudaStream_t st, int phase) {
     vvb200_device_state *d = p->dev;
     const int numTiles = d->numTiles;
     const int C = std::max(1, std::min(std::min(envInt("VVB200_HOST_CHUNKS", 8), 64), numTiles));
@@ -1970,9 +1973,11 @@ static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb
         d->pipeEvents.push_back(e);
     }
     cudaEvent_t *evA = d->pipeEvents.data(), *evB = evA + C, *evC = evB + C, evStart = evC[C], evDone = evC[C + 1];
-    CUDA_TRY(cudaEventRecord(evStart, st));
-    CUDA_TRY(cudaStreamWaitEvent(d->sIn, evStart, 0));
-    CUDA_TRY(cudaStreamWaitEvent(d->sOut, evStart, 0));
+    if (phase != 2) {
+        CUDA_TRY(cudaEventRecord(evStart, st));
+        CUDA_TRY(cudaStreamWaitEvent(d->sIn, evStart, 0));
+        CUDA_TRY(cudaStreamWaitEvent(d->sOut, evStart, 0));
+    }
     auto tileLo = [&](int c) { return (int) ((long long) numTiles * c / C); };
     auto partLo = [&](int c) { return c >= C ? P : (size_t) p->tileStart[tileLo(c)]; };   // the last chunk takes the padding
     char *dVelm = (char *) d->hVelm, *dPosq = (char *) d->hPosq, *dCorr = (char *) d->hCorr;
@@ -1985,7 +1990,7 @@ static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb
     const bool cosine = p->par.cos_acceleration != 0;
     const bool extra = cosine || !p->particlesElectrolyte.empty();   // pass A then reads posq too
     // ---- velocities + forces in, pass A chunk by chunk ----
-    for (int c = 0; c < C; c++) {
+    for (int c = 0; c < C && phase != 2; c++) {
         const size_t lo = partLo(c), n = partLo(c + 1) - lo;
         CUDA_TRY(cudaMemcpyAsync(dVelm + lo * ms, (const char *) hb->velm + lo * ms, n * ms, cudaMemcpyHostToDevice, d->sIn));
         for (int k = 0; k < 3; k++)
@@ -2001,20 +2006,29 @@ static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb
         k.tileBegin = tileLo(c);
         k.tileEnd = tileLo(c + 1);
         k.accumulateRed = c > 0;
-        k.fuseNHC = hasNH(p) && c == C - 1;
+        k.fuseNHC = hasNH(p) && c == C - 1 && phase == 0;
         CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, cosine, k, d->numSM, st)));
         p->launches++;
     }
-    // ---- positions in, pass B, results out ----
+    // ---- positions in (queued behind the velocities: the copy engine keeps going while the sums are exchanged) ----
+    for (int c = 0; c < C && phase != 2 && !extra; c++) {
+        const size_t lo = partLo(c), n = partLo(c + 1) - lo;
+        CUDA_TRY(cudaMemcpyAsync(dPosq + lo * rs, (const char *) hb->posq + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
+        if (mixedMode)
+            CUDA_TRY(cudaMemcpyAsync(dCorr + lo * rs, (const char *) hb->posq_correction + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
+        CUDA_TRY(cudaEventRecord(evB[c], d->sIn));
+    }
+    if (phase == 1)
+        return VVB200_OK;
+    if (phase == 2 && hasNH(p)) {
+        int rc = launchNhc(p, st);      // all-reduce over NVLink peer memory (when attached) + NH chains
+        if (rc) return rc;
+    }
+    // ---- pass B, results out ----
     for (int c = 0; c < C; c++) {
         const size_t lo = partLo(c), n = partLo(c + 1) - lo;
-        if (!extra) {
-            CUDA_TRY(cudaMemcpyAsync(dPosq + lo * rs, (const char *) hb->posq + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
-            if (mixedMode)
-                CUDA_TRY(cudaMemcpyAsync(dCorr + lo * rs, (const char *) hb->posq_correction + lo * rs, n * rs, cudaMemcpyHostToDevice, d->sIn));
-            CUDA_TRY(cudaEventRecord(evB[c], d->sIn));
+        if (!extra)
             CUDA_TRY(cudaStreamWaitEvent(st, evB[c], 0));
-        }
         KParams k = makeParams(p, &db, a);
         k.tileBegin = tileLo(c);
         k.tileEnd = tileLo(c + 1);
@@ -2031,6 +2045,61 @@ static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb
     CUDA_TRY(cudaStreamWaitEvent(st, evDone, 0));
     CUDA_TRY(cudaStreamSynchronize(st));
     return VVB200_OK;
+}
+
+static int ensureStaging(vvb200_plan *p) {
+    vvb200_device_state *d = p->dev;
+    const size_t P = p->paddedN;
+    const size_t ms = mixedSize(p->precision), rs = realSize(p->precision);
+    if (d->stagedN != P) {
+        CUDA_TRY(cudaMalloc(&d->hPosq, P * 4 * rs)); d->allocations.push_back(d->hPosq);
+        CUDA_TRY(cudaMalloc(&d->hCorr, P * 4 * rs)); d->allocations.push_back(d->hCorr);
+        CUDA_TRY(cudaMalloc(&d->hVelm, P * 4 * ms)); d->allocations.push_back(d->hVelm);
+        CUDA_TRY(cudaMalloc((void **) &d->hForce, P * 3 * sizeof(long long))); d->allocations.push_back(d->hForce);
+        d->stagedN = P;
+    }
+    return VVB200_OK;
+}
+
+static bool pipelineEligible(const vvb200_plan *p) {
+    return p->tiled && p->par.use_middle_scheme && p->imagePairs.empty() && p->particlesLD.empty();
+}
+
+static int checkHostSplit(vvb200_plan *p, const vvb200_buffers *hb, const char *who) {
+    if (!p || !hb) {
+        vvb200_set_error("%s: null argument", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!p->dev) {
+        vvb200_set_error("%s: plan not uploaded (call vvb200_plan_upload)", who);
+        return VVB200_ERR_NOT_UPLOADED;
+    }
+    if (!pipelineEligible(p)) {
+        vvb200_set_error("%s: needs the tiled middle-scheme path without Langevin or image particles", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!hb->velm || !hb->posq || !hb->force || (p->precision == VVB200_MIXED && !hb->posq_correction)) {
+        vvb200_set_error("%s: missing host buffer", who);
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    return VVB200_OK;
+}
+
+extern "C" int vvb200_step_host_begin(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, void *stream) {
+    int rc = checkHostSplit(p, hb, "vvb200_step_host_begin");
+    if (rc) return rc;
+    if ((rc = ensureStaging(p))) return rc;
+    return stepHostPipelined(p, hb, a, (cudaStream_t) stream, 1);
+}
+
+extern "C" int vvb200_step_host_finish(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, void *stream) {
+    int rc = checkHostSplit(p, hb, "vvb200_step_host_finish");
+    if (rc) return rc;
+    if (p->dev->stagedN != (size_t) p->paddedN) {
+        vvb200_set_error("vvb200_step_host_finish: call vvb200_step_host_begin first");
+        return VVB200_ERR_INVALID_ARGUMENT;
+    }
+    return stepHostPipelined(p, hb, a, (cudaStream_t) stream, 2);
 }
 
 extern "C" int vvb200_step_host(vvb200_plan *p, const vvb200_buffers *hb, const vvb200_step_args *a, int steps, void *stream) {
@@ -2050,18 +2119,13 @@ extern "C" int vvb200_step_host(vvb200_plan *p, const vvb200_buffers *hb, const 
     vvb200_device_state *d = p->dev;
     const size_t P = p->paddedN;
     const size_t ms = mixedSize(p->precision), rs = realSize(p->precision);
-    if (d->stagedN != P) {
-        CUDA_TRY(cudaMalloc(&d->hPosq, P * 4 * rs)); d->allocations.push_back(d->hPosq);
-        CUDA_TRY(cudaMalloc(&d->hCorr, P * 4 * rs)); d->allocations.push_back(d->hCorr);
-        CUDA_TRY(cudaMalloc(&d->hVelm, P * 4 * ms)); d->allocations.push_back(d->hVelm);
-        CUDA_TRY(cudaMalloc((void **) &d->hForce, P * 3 * sizeof(long long))); d->allocations.push_back(d->hForce);
-        d->stagedN = P;
-    }
+    int rc = ensureStaging(p);
+    if (rc) return rc;
     const bool mixedMode = p->precision == VVB200_MIXED;
     // one step of a large tiled system: overlap copy-in, the two passes and copy-out (VVB200_HOST_PIPELINE=0 disables)
-    if (steps == 1 && p->tiled && p->par.use_middle_scheme && p->imagePairs.empty() &&
-        p->N >= envInt("VVB200_HOST_PIPELINE_MIN", 1000000) && envInt("VVB200_HOST_PIPELINE", 1))
-        return stepHostPipelined(p, hb, a, st);
+    if (steps == 1 && pipelineEligible(p) && p->N >= envInt("VVB200_HOST_PIPELINE_MIN", 1000000) &&
+        envInt("VVB200_HOST_PIPELINE", 1))
+        return stepHostPipelined(p, hb, a, st, 0);
     CUDA_TRY(cudaMemcpyAsync(d->hVelm, hb->velm, P * 4 * ms, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->hForce, hb->force, P * 3 * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->hPosq, hb->posq, P * 4 * rs, cudaMemcpyHostToDevice, st));

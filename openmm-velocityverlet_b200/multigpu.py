@@ -106,3 +106,12 @@ class DistributedPlan:
             dist.all_reduce(self._red, group=self.group)           # NCCL: the only exchange, <= 10 doubles
         # peer path: the exchange happens inside the single-block NH-chain kernel, over cudaIpc-mapped NVLink memory
         self.plan.middle_nhc_scale_drift(bufs, **kw)
+
+    def step_host(self, host_state, **kw):
+        """one step through HOST buffers (pinned for full speed): copy-in, pass A, exchange, pass B and copy-out overlapped
+        chunk by chunk (vvb200_step_host_begin / _finish)"""
+        import torch.distributed as dist
+        self.plan.step_host_begin(host_state, **kw)
+        if not self.peer and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self._red, group=self.group)
+        self.plan.step_host_finish(host_state, **kw)

@@ -66,6 +66,17 @@ def main():
             ok = max(ev, ex) < 1e-9 and max(ek, es) < 1e-12
             print(f"[{name}] world={world} N={spec.n}: v {ev:.2e} x {ex:.2e} ke2 {ek:.2e} vscale {es:.2e} "
                   f"bias {st['velocity_bias']:.6e}/{sw['velocity_bias']:.6e} -> {'OK' if ok else 'FAIL'}", flush=True)
+        # the same steps through HOST buffers (pipelined copy-in / pass A / exchange / pass B / copy-out) on a second plan
+        os.environ["VVB200_HOST_CHUNKS"] = "4"
+        dp2 = vv.DistributedPlan(local_spec, params, "mixed").upload(peer={"auto": None, "nccl": False, "peer": True}[mode])
+        hs = lstate.copy()
+        for _ in range(steps):
+            dp2.step_host(hs, inv_box_z=inv_box_z)
+        eh = max(rel_err(hs.velm[: b - a, :3], got.velm[: b - a, :3]), rel_err(hs.positions()[: b - a], got.positions()[: b - a]))
+        host_ok = eh < 1e-11
+        ok = ok and host_ok
+        if rank == 0:
+            print(f"[{name}] host-buffer pipeline vs device-resident steps: {eh:.2e} -> {'OK' if host_ok else 'FAIL'}", flush=True)
         # scale factors identical on every rank
         t = torch.tensor(st["vscale"], device="cuda", dtype=torch.float64)
         g = [torch.zeros_like(t) for _ in range(world)]
