@@ -4,13 +4,15 @@
 // launches).  VVIntegrator.cpp keeps calling the same virtuals in the same order (VVIntegrator.cpp:232-338); each
 // one maps onto the C ABI as follows.
 //
-// Middle scheme, no OpenMM constraints / virtual sites in the System (the fused fast path, 2 launches per step):
-//   resetExtraForce / applyElectricForce / applyCosineForce      no-ops: extra forces are evaluated inside pass A
+// Middle scheme, no OpenMM constraints / virtual sites in the System (the fused fast path: ONE launch per step while
+// the system fits in shared memory, ~100k particles; two streaming passes beyond that):
+//   resetExtraForce / applyElectricForce / applyCosineForce      no-ops: extra forces are evaluated inside the kick
 //   applyLangevinForce                                            prepareRandomNumbers (same request size) only
-//   firstIntegrate                                                vvb200_middle_kick_reduce      (pass A)
-//   calc/remove/restoreVelocityBias, scaleVelocity                no-ops: folded into the two passes
-//   secondIntegrate                                               vvb200_middle_nhc_scale_drift  (NH chains + pass B)
-//   updateImagePositions                                          vvb200_update_image_positions
+//   firstIntegrate                                                no-op (nothing of OpenMM's runs before secondIntegrate)
+//   calc/remove/restoreVelocityBias, scaleVelocity                no-ops: folded into the step
+//   secondIntegrate                                               vvb200_step_middle  (kick + reductions + NH chains +
+//                                                                 scale + drift + hard wall + image mirror)
+//   updateImagePositions                                          no-op (done by vvb200_step_middle)
 // With constraints or virtual sites OpenMM's solvers must run between the sub-steps, so the split entry points are
 // used: kick -> applyVelocityConstraints | (no-op) | thermostat_delta -> applyConstraints -> finish  (440 B/particle).
 // Velocity-Verlet scheme: thermostat | vv_kick(+posDelta) -> applyConstraints -> vv_positions | vv_kick | thermostat.
@@ -188,10 +190,8 @@ void CudaIntegrateMiddleStepKernel::firstIntegrate(ContextImpl &, const VVIntegr
     syncStepSize(*sh, integrator);
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);
-    if (!sh->constrained) {
-        VVB200_CHECK(vvb200_middle_kick_reduce(sh->plan, &b, &a, cu.getCurrentStream()));
-        return;
-    }
+    if (!sh->constrained)
+        return;        // the whole step runs in secondIntegrate (vvb200_step_middle): no OpenMM solver sits in between
     VVB200_CHECK(vvb200_middle_kick(sh->plan, &b, &a, cu.getCurrentStream()));
     cu.getIntegrationUtilities().applyVelocityConstraints(integrator.getConstraintTolerance());
 }
@@ -202,7 +202,7 @@ void CudaIntegrateMiddleStepKernel::secondIntegrate(ContextImpl &, const VVInteg
     vvb200_step_args a = stepArgs(cu, *sh, integrator);
     CudaIntegrationUtilities &integration = cu.getIntegrationUtilities();
     if (!sh->constrained) {
-        VVB200_CHECK(vvb200_middle_nhc_scale_drift(sh->plan, &b, &a, cu.getCurrentStream()));
+        VVB200_CHECK(vvb200_step_middle(sh->plan, &b, &a, cu.getCurrentStream()));
     } else {
         // thermostat (bias remove / restore included) + both half drifts into posDelta / oldDelta, fused
         VVB200_CHECK(vvb200_middle_thermostat_delta(sh->plan, &b, &a, cu.getCurrentStream()));
@@ -285,7 +285,7 @@ void CudaModifyImageChargeKernel::initialize(const System &, const VVIntegrator 
 
 void CudaModifyImageChargeKernel::updateImagePositions(ContextImpl &, const VVIntegrator &integrator) {
     if (integrator.getUseMiddleScheme() && !sh->constrained)
-        return;                             // vvb200_middle_nhc_scale_drift already mirrored the images
+        return;                             // vvb200_step_middle already mirrored the images
     ContextSelector selector(cu);
     vvb200_buffers b = deviceBuffers(cu);
     VVB200_CHECK(vvb200_update_image_positions(sh->plan, &b, cu.getCurrentStream()));
