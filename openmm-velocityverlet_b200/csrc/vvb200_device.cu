@@ -975,13 +975,31 @@ static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stage
     return c;
 }
 
+// The two streaming kernels are launched with programmatic stream serialization (PDL): each may be scheduled while
+// its predecessor drains (last-block reduction, NH chains, store tail) and waits at its own gridDepWait() before
+// touching data -- the ~2-3 us of launch latency and prologue per kernel leave the critical path (VVB200_PDL=0: off).
+template <class... Args>
+static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, size_t smem, cudaStream_t st, const KParams &k) {
+    static const int pdl = envInt("VVB200_PDL", 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(BTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, k);
+}
+
 template <int MODE, int KICK, bool EXTRA>
 static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
     static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", MINBLOCKS_A);
     k.stagesA = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
-    kick_reduce_kernel<MODE, KICK, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
-    return cudaGetLastError();
+    return launchStreaming(kick_reduce_kernel<MODE, KICK, EXTRA>, grid, cfg.smem, st, k);
 }
 
 template <int MODE, int VARIANT, bool EXTRA>
@@ -989,8 +1007,7 @@ static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
     static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", MINBLOCKS_B);
     k.stagesB = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
-    scale_drift_kernel<MODE, VARIANT, EXTRA><<<grid, BTHREADS, cfg.smem, st>>>(k);
-    return cudaGetLastError();
+    return launchStreaming(scale_drift_kernel<MODE, VARIANT, EXTRA>, grid, cfg.smem, st, k);
 }
 
 // EXTRA kernels stage posq as well: needed by the external field (charge), the cosine acceleration (z) and, for

@@ -330,6 +330,31 @@ extern "C" int vvb200_plan_create(const vvb200_system *sys, const vvb200_params 
 // VVB200_TILE_CAP slots that never separates (a) the massive-or-thermostatted particles of one
 // thermostat molecule when the COM temperature group is on, or (b) the two particles of a Drude
 // pair.  Returns false (with tiledWhyNot set) if the topology cannot be tiled that way.
+// Nearly equal tiles whose count is a multiple of 888 (see buildTiles).  cover[i] != 0: no cut between slots i-1 and i;
+// molBefore: prefix count of thermostat molecules.  Returns false when no such partition respects the tile limits.
+static bool buildBalancedTiles(vvb200_plan *p, const std::vector<int32_t> &cover, const std::vector<int32_t> &molBefore) {
+    const int N = p->N;
+    const int unit = 888;
+    for (int T = (N / VVB200_TILE_CAP / unit + 1) * unit; (double) N / T >= 192.0; T += unit) {
+        p->tileStart.assign(1, 0);
+        bool ok = true;
+        for (int i = 1; i <= T && ok; i++) {
+            int32_t e = i == T ? N : (int32_t) ((long long) N * i / T);
+            while (e > p->tileStart.back() && e < N && cover[e] != 0)
+                e--;
+            const int32_t s = p->tileStart.back();
+            if (e <= s || e - s > VVB200_TILE_CAP || molBefore[e] - molBefore[s] > VVB200_TILE_MAX_MOLS)
+                ok = false;
+            else
+                p->tileStart.push_back(e);
+        }
+        if (ok)
+            return true;
+    }
+    p->tileStart.clear();
+    return false;
+}
+
 static bool buildTiles(vvb200_plan *p) {
     const int N = p->N, M = p->M;
     const bool useCOM = p->par.use_com_temp_group != 0;
@@ -408,7 +433,17 @@ static bool buildTiles(vvb200_plan *p) {
             cap = std::min(VVB200_TILE_CAP, std::max(128, (perBlock + 31) / 32 * 32));
         }
     }
-    for (;;) {
+    // Experiment kept behind VVB200_BALANCED_TILES=1 (off): the persistent grids of pass A (3 x 148 blocks) and pass B
+    // (2 x 148) assign tiles round-robin, so mid-size systems leave part of the machine idle for a tile at the end
+    // (1M particles: 4.5 tiles per pass-A block).  Cutting into a multiple of lcm(444, 296) = 888 equal tiles removes
+    // that -- and measured SLOWER on B200 (1M: 68.4 vs 65.0 us per step, 4M: 184.5 vs 179.9): the smaller tiles' fixed
+    // per-tile cost (barriers, pipeline hand-offs) outweighs the imbalance.
+    bool balanced = false;
+    if (cap == VVB200_TILE_CAP && N <= 12000000) {
+        const char *env = getenv("VVB200_BALANCED_TILES");
+        balanced = env && atoi(env) != 0 && buildBalancedTiles(p, cover, molBefore);
+    }
+    while (!balanced) {
         p->tileStart.clear();
         p->tileStart.push_back(0);
         int32_t s = 0;

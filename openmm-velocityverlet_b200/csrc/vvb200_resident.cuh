@@ -110,9 +110,8 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             if (Stage::CORR) bulkLoad(st.corr, reinterpret_cast<const real4 *>(p.corr) + a0, cnt * (uint32_t) sizeof(real4), full + j);
         }
     }
-    static_assert(sizeof(NhcDevice) % 8 == 0 && sizeof(NhcDevice) / 8 <= CTHREADS, "NhcDevice copy");
-    if (p.doReduce && tid >= 32 && tid < 32 + (int) (sizeof(NhcDevice) / 8))
-        reinterpret_cast<double *>(&nhcS)[tid - 32] = __ldcg(reinterpret_cast<const double *>(p.nhc) + (tid - 32));
+    if (p.doReduce)
+        nhcFetch(&nhcS, p.nhc, tid, 32);
     __syncthreads();
     traceMark(1);
 
@@ -149,8 +148,7 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
         if (last) {
             lastBlockFinish<NR>(p, sm, cosine, tid, &nhcS);
             consumerBarrier();
-            if (tid < (int) (sizeof(NhcDevice) / 8))      // the advanced state back to global memory
-                reinterpret_cast<double *>(p.nhc)[tid] = reinterpret_cast<const double *>(&nhcS)[tid];
+            nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
             consumerBarrier();        // the release below is cumulative over what the barrier ordered before it
             if (tid == 0) st_release_gpu(p.gridGen, gen0 + 1u);
         } else if (tid == 0) {

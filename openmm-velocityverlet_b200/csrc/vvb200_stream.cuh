@@ -76,6 +76,12 @@ __device__ __forceinline__ void bulkLoad(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
                  "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream is still draining; it must not touch the predecessor's data before
+// gridDepWait() (which returns once that grid has completed and its writes are visible).  gridDepLaunch() tells the
+// runtime that this block no longer needs to hold the successor back.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void gridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gridDepLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void consumerBarrier() { asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory"); }
 
 // tile descriptor (two int4 per tile, built by vvb200_plan_upload)
@@ -354,6 +360,19 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
     }
 }
 
+// NhcDevice <-> shared-memory copy by threads first .. first + sizeof/8 - 1 (plain 8-byte words; __ldcg: the source may
+// have been written by another SM earlier in this launch sequence)
+static_assert(sizeof(NhcDevice) % 8 == 0 && sizeof(NhcDevice) / 8 <= CTHREADS - 32, "NhcDevice copy");
+__device__ __forceinline__ void nhcFetch(NhcDevice *shared, const NhcDevice *global, const int tid, const int first) {
+    const int i = tid - first;
+    if (i >= 0 && i < (int) (sizeof(NhcDevice) / 8))
+        reinterpret_cast<double *>(shared)[i] = __ldcg(reinterpret_cast<const double *>(global) + i);
+}
+__device__ __forceinline__ void nhcStore(NhcDevice *global, const NhcDevice *shared, const int tid) {
+    if (tid < (int) (sizeof(NhcDevice) / 8))
+        reinterpret_cast<double *>(global)[tid] = reinterpret_cast<const double *>(shared)[tid];
+}
+
 // ---- per-block reduction of the thread accumulators (fixed order) and the arrival ticket: true for the block
 //      that arrives last.  All CTHREADS consumer threads call it. -------------------------------------------------
 template <int NR, class Scratch, class mixed>
@@ -442,6 +461,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
     typedef StageA<MODE, EXTRA> Stage;
     typedef ScratchA<MODE, EXTRA> Scratch;
     extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ NhcDevice nhcS;
     const int stages = p.stagesA;
     constexpr size_t stageBytes = roundUp128(sizeof(Stage));
     Scratch &sm = *reinterpret_cast<Scratch *>(smemRaw + stageBytes * stages);
@@ -457,6 +477,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
         fenceBarrierInit();
     }
     __syncthreads();
+    gridDepWait();      // PDL: everything above overlapped the previous kernel's tail (pass B of the step before)
 
     const bool cosine = EXTRA && p.cosine;
     const bool useCOM = p.useCOM;
@@ -493,6 +514,10 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
     }
 
     // ===== consumers =====
+    // every block prefetches the thermostat state (any of them may arrive last): the chains then run on shared memory
+    // instead of a string of dependent L2 round trips
+    if (p.fuseNHC)
+        nhcFetch(&nhcS, p.nhc, tid, 0);
     const ACtx<MODE> c = makeACtx<MODE, KICK>(p, EXTRA);
     constexpr int NR = EXTRA ? VVB200_NRED : 3;
     // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
@@ -521,9 +546,16 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
         buf ^= 1;
     }
 
+    if (tid == 0) gridDepLaunch();      // this block's tiles are done: pass B may start being scheduled
     if (!blockReduceAndTicket<NR>(p, sm, acc, tid))
         return;
-    lastBlockFinish<NR>(p, sm, cosine, tid);
+    if (p.fuseNHC) {
+        lastBlockFinish<NR>(p, sm, cosine, tid, &nhcS);
+        consumerBarrier();
+        nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
+    } else {
+        lastBlockFinish<NR>(p, sm, cosine, tid);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -956,6 +988,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
         fenceBarrierInit();
     }
     __syncthreads();
+    gridDepWait();      // PDL: everything above overlapped pass A's last-block reduction and NH chains
 
     const bool cosine = EXTRA && p.cosine;
     const bool useCOM = p.useCOM;
@@ -1024,4 +1057,5 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
         mbarArrive(empty + s);   // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
     }
+    if (tid == 0) gridDepLaunch();      // the next kernel in the stream (next step's pass A) may be scheduled
 }

@@ -27,6 +27,11 @@ for name, fn, bytes_ in (("kick (kickOnly)", lambda: plan.middle_kick(b), 92),
                          ("delta(1)", lambda: plan.middle_delta(b, 1), 160),
                          ("thermostat (reduce + scale)", lambda: plan.thermostat(b), 36 + 68),
                          ("vv_positions + hardwall", lambda: plan.vv_positions(b), 160 + 23),
+                         ("measure_temperatures (reduce only)", lambda: plan.measure_temperatures(b), 36),
+                         ("step_vv_first (reduce + scale/kick/drift)", lambda: plan.step_vv_first(b), 36 + 156),
+                         ("step_vv_second (kick+reduce + scale)", lambda: plan.step_vv_second(b), 92 + 68),
                          ("step_middle fused", lambda: plan.step_middle(b), 224)):
+    if len(sys.argv) > 1 and not any(a in name for a in sys.argv[1:]):
+        continue
     ms = timed(fn)
     print(f"{name:42s} {ms*1e3:8.1f} us  {bytes_ * N / ms / 1e6:8.0f} GB/s (model {bytes_} B/particle)")
