@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-config2", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="multi-GPU exchange of the 10-double reduction vector: NVLink peer memory inside the NHC kernel, or NCCL")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
@@ -221,7 +222,7 @@ def pinned_state(vv, host):
     return st
 
 
-def small_system_leg(vv, torch, precision, n_ip=1250, steps=400):
+def small_system_leg(vv, torch, precision, n_ip=1250, steps=400, graph=True):
     """BASELINE configs[1]: 1,250 ion pairs = 46,250 particles, TGNH, middle scheme, hard wall.  The whole step is ONE
     launch (csrc/vvb200_resident.cuh); timed eagerly through the C ABI and replayed from a CUDA graph."""
     spec = vv.make_bulk_ionic_liquid(n_ip)
@@ -245,6 +246,8 @@ def small_system_leg(vv, torch, precision, n_ip=1250, steps=400):
     resident = (plan.resident_launch_count - r0) / steps
     graph_us = None
     try:
+        if not graph:
+            raise RuntimeError("not requested")
         side = torch.cuda.Stream()
         side.wait_stream(st)
         with torch.cuda.stream(side):
@@ -266,7 +269,7 @@ def small_system_leg(vv, torch, precision, n_ip=1250, steps=400):
         graph_us = f"capture failed: {e}"
     return {"workload": f"BASELINE configs[1]: Drude ionic-liquid bulk, {n_ip} ion pairs = {spec.n} particles, TGNH 3 groups, "
                         f"middle scheme, hard wall, {precision}",
-            "us_per_step": eager_us, "cuda_graph_us_per_step": graph_us, "launches_per_step": launches,
+            "particles": spec.n, "us_per_step": eager_us, "cuda_graph_us_per_step": graph_us, "launches_per_step": launches,
             "single_launch_resident_steps_per_step": resident,
             "value": spec.n / (eager_us * 1e-6), "unit": UNIT,
             "note": "latency-bound (1.5 MB of state): no roofline fraction; the reference's kernels need 10 launches + a "
@@ -318,8 +321,12 @@ def main():
         one_step()
     barrier()
 
-    # ---- device-resident timing -------------------------------------------------------------
-    plan.profile_enable(K)
+    # ---- device-resident timing: EXACTLY K steps between two events on the launching stream.  The first K/5 of them
+    #      also carry an event pair around every launch (vvb200_profile_*) for the per-kernel roofline; only a sample,
+    #      because an event between two launches forbids the overlap of pass B's launch with pass A's tail
+    #      (programmatic dependent launch): ~2 % of a 16M-particle step, ~25 % of a 1M-particle one. --------------
+    prof_n = max(1, K // 5)
+    plan.profile_enable(prof_n)
     launches0 = plan.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -355,6 +362,8 @@ def main():
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["bytes_per_particle"] * n_local,
                 "kernels": [ka, kb],
+                "kernel_timing": f"CUDA events recorded by the library on the launching stream around every launch of the first "
+                                 f"{prof_steps} of the {K} timed steps (events between launches forbid launch overlap)",
                 "step_gbs": (BYTES_PASS_A + BYTES_PASS_B) * n_local / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": (BYTES_PASS_A + BYTES_PASS_B) * n_local / (ms_per_step * 1e-3) / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
@@ -429,6 +438,17 @@ def main():
     if rank == 0 and world == 1 and not args.no_config2:
         config2 = small_system_leg(vv, torch, args.precision)
 
+    # ---- the >= 1M-particle target of BASELINE.json at other sizes (rank 0, single-GPU runs): whole-step time and
+    #      the fraction of the HBM peak the 216 algorithmic bytes per particle amount to -------------------------
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        sweep = []
+        for n_ip in (27648, 110592):
+            r = small_system_leg(vv, torch, args.precision, n_ip=n_ip, steps=200, graph=False)
+            gbs = (BYTES_PASS_A + BYTES_PASS_B) * r["particles"] / (r["us_per_step"] * 1e-6) / 1e9
+            sweep.append({"particles": r["particles"], "us_per_step": r["us_per_step"], "launches_per_step": r["launches_per_step"],
+                          "step_gbs": gbs, "step_frac": gbs / peak})
+
     # ---- CPU baseline (rank 0, single-GPU runs only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -448,7 +468,7 @@ def main():
                                         "NCCL all-reduce of 10 doubles") if world > 1 else "none"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "reference_kernels_on_gpu": ref_gpu,
-                "config2_small_system": config2,
+                "config2_small_system": config2, "size_sweep": sweep,
                 "clocks": clocks.summary(),
                 "integrator_only_ns_per_day": 86400.0 / (ms_per_step * 1e-3) * params.step_size * 1e-3,
                 "thermostat": {"ke2": [float(x) for x in st["ke2"]], "vscale": [float(x) for x in st["vscale"]]}}
