@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
                     help="multi-GPU exchange of the 10-double reduction vector: NVLink peer memory inside the NHC kernel, or NCCL")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=90.0, help="budget of the whole --impl reference run")
     return ap.parse_args()
 
 
@@ -184,7 +185,7 @@ def run_reference_arm(args):
         return
     vv = entry.load_package()
     vo = entry.load_oracle()
-    value, ms, info = cpu_arm(vv, vo, args, args.steps, args.warmup, seconds_budget=90.0)
+    value, ms, info = cpu_arm(vv, vo, args, args.steps, args.warmup, seconds_budget=args.ref_seconds)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -953,7 +953,8 @@ static int envInt(const char *name, int dflt) {
 struct LaunchCfg { int stages, perSM; size_t smem; };
 
 template <class F>
-static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stagesEnv, const char *blocksEnv, int dfltBlocks) {
+static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stagesEnv, const char *blocksEnv, int dfltBlocks,
+                           int blockThreads, int maxStages) {
     int dev = 0, maxOptin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -963,14 +964,14 @@ static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stage
     int stages = envInt(stagesEnv, 0);
     if (stages <= 0) {
         stages = 1;
-        while (stages < 8 && (smemBytes(stages + 1) + 1024) * c.perSM <= perSMBudget) stages++;
+        while (stages < maxStages && (smemBytes(stages + 1) + 1024) * c.perSM <= perSMBudget) stages++;
     }
     while (stages > 1 && smemBytes(stages) > (size_t) maxOptin) stages--;
     c.stages = stages;
     c.smem = smemBytes(stages);
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BTHREADS, c.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, blockThreads, c.smem);
     c.perSM = std::max(1, std::min(c.perSM, occ));
     return c;
 }
@@ -979,11 +980,11 @@ static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stage
 // its predecessor drains (last-block reduction, NH chains, store tail) and waits at its own gridDepWait() before
 // touching data -- the ~2-3 us of launch latency and prologue per kernel leave the critical path (VVB200_PDL=0: off).
 template <class... Args>
-static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, size_t smem, cudaStream_t st, const KParams &k) {
+static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, int blockThreads, size_t smem, cudaStream_t st, const KParams &k) {
     static const int pdl = envInt("VVB200_PDL", 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(BTHREADS);
+    cfg.blockDim = dim3(blockThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -996,18 +997,21 @@ static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, size_t sme
 
 template <int MODE, int KICK, bool EXTRA>
 static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
-    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", MINBLOCKS_A);
+    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", MINBLOCKS_A, BTHREADS, 8);
     k.stagesA = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
-    return launchStreaming(kick_reduce_kernel<MODE, KICK, EXTRA>, grid, cfg.smem, st, k);
+    return launchStreaming(kick_reduce_kernel<MODE, KICK, EXTRA>, grid, BTHREADS, cfg.smem, st, k);
 }
 
 template <int MODE, int VARIANT, bool EXTRA>
 static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
-    static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", MINBLOCKS_B);
+    // the scale-only variant stages 36 B/particle instead of 68: it needs a deeper ring for the same bytes in flight
+    constexpr int maxStages = VARIANT == VAR_SCALE_ONLY ? 8 : MAXSTAGES_B;
+    constexpr int blockThreads = passBConsumers(VARIANT) + 32;
+    static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", passBMinBlocks(VARIANT), blockThreads, maxStages);
     k.stagesB = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
-    return launchStreaming(scale_drift_kernel<MODE, VARIANT, EXTRA>, grid, cfg.smem, st, k);
+    return launchStreaming(scale_drift_kernel<MODE, VARIANT, EXTRA>, grid, blockThreads, cfg.smem, st, k);
 }
 
 // EXTRA kernels stage posq as well: needed by the external field (charge), the cosine acceleration (z) and, for

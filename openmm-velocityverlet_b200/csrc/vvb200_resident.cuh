@@ -48,7 +48,9 @@ __device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) 
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifndef RESIDENT_MINBLOCKS
 #define RESIDENT_MINBLOCKS 2
+#endif
 
 template <int MODE, int KICK, int VARIANT, bool EXTRA>
 __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_kernel(const KParams p) {
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
         if (tile >= p.numTiles) break;
         mbarWait(full + j, 0);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * j);
-        passBTile<MODE, VARIANT, EXTRA>(p, cb, st, tid);
+        passBTile<MODE, VARIANT, EXTRA, CTHREADS>(p, cb, st, tid);
     }
     traceMark(6);
 }

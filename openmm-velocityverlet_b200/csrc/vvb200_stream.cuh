@@ -24,13 +24,21 @@
 #ifndef MINBLOCKS_A
 #define MINBLOCKS_A 3                         // pass A: 3 co-resident blocks (<= 72 registers) hide its block barriers
 #endif
-#ifndef MINBLOCKS_B
-#define MINBLOCKS_B 2
+// pass B: ONE block per SM with 16 consumer warps (one particle per thread) and a 4-deep ring.  Measured against two
+// blocks of 8 consumer warps with 2 stages each (same warps, same shared memory): 341.6 vs 362 us for 16.4M particles
+// -- a tile is finished in half the time, so the stage goes back to the producer sooner and three tiles instead of
+// one are in flight behind the one being computed.
+// The scale-only variant (64 B/particle, little arithmetic) is the exception: two independent 8-warp blocks overlap
+// one block's wait with the other's stores better than one wide block does (156 vs 178 us), so the consumer count is a
+// template parameter of the kernel and chosen per variant (passBConsumers).
+#ifndef MAXSTAGES_B
+#define MAXSTAGES_B 4
 #endif
-#define ITEMS (VVB200_TILE_CAP / CTHREADS)
+__host__ __device__ constexpr int passBConsumers(int variant) { return variant == VAR_SCALE_ONLY ? 256 : 512; }
+__host__ __device__ constexpr int passBMinBlocks(int variant) { return variant == VAR_SCALE_ONLY ? 2 : 1; }
+#define ITEMS ((VVB200_TILE_CAP + CTHREADS - 1) / CTHREADS)   // particles per consumer thread (the last round may be partial)
 #define PADT (VVB200_TILE_CAP + 8)            // stage slots: tile + alignment slack
 #define MAXMOL VVB200_TILE_MAX_MOLS
-static_assert(VVB200_TILE_CAP % CTHREADS == 0, "tile must be a multiple of the consumer count");
 static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
 
 // -DVVB200_TRACE (diagnostic builds only, tests/diag_trace.py): %globaltimer stamps of thread 0 of every block
@@ -641,8 +649,10 @@ template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams
 }
 
 // One tile of pass B from a filled stage (used by the streaming kernel below and the resident kernel).
-template <int MODE, int VARIANT, bool EXTRA, class Stage>
+// CT = consumer threads working on the tile (each takes ceil(tile / CT) particles)
+template <int MODE, int VARIANT, bool EXTRA, int CT, class Stage>
 __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx, Stage &st, const int tid) {
+    constexpr int ITEMS_B = (VVB200_TILE_CAP + CT - 1) / CT;
     typedef Prec<MODE> P;
     typedef typename P::real real;
     typedef typename P::mixed mixed;
@@ -663,8 +673,8 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
     const int sl0 = t0 - (t0 & ~3);
 
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        const int loc = it * CTHREADS + tid;
+    for (int it = 0; it < ITEMS_B; it++) {
+        const int loc = it * CT + tid;
         const int idx = t0 + loc, sl = sl0 + loc;
         if (idx >= t1) continue;
         const uint32_t mw = st.meta[sl];
@@ -965,7 +975,8 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
 }
 
 template <int MODE, int VARIANT, bool EXTRA>
-__global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(const KParams p) {
+__global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(VARIANT)) scale_drift_kernel(const KParams p) {
+    constexpr int CTHREADS_B = passBConsumers(VARIANT);
     typedef Prec<MODE> P;
     typedef typename P::real real;
     typedef typename P::mixed mixed;
@@ -983,7 +994,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     if (tid == 0) {
         for (int s = 0; s < stages; s++) {
             mbarInit(full + s, 1);
-            mbarInit(empty + s, CTHREADS);
+            mbarInit(empty + s, CTHREADS_B);
         }
         fenceBarrierInit();
     }
@@ -993,9 +1004,9 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     const bool cosine = EXTRA && p.cosine;
     const bool useCOM = p.useCOM;
 
-    if (tid >= CTHREADS) {
+    if (tid >= CTHREADS_B) {
         // ===== producer warp (all lanes stay: the gather fallback uses them) =====
-        const int lane = tid - CTHREADS;
+        const int lane = tid - CTHREADS_B;
         const mixed4 *comV = reinterpret_cast<const mixed4 *>(p.comV);
         const mixed *comCbar = reinterpret_cast<const mixed *>(p.comCbar);
         int s = 0;
@@ -1053,7 +1064,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_B) scale_drift_kernel(cons
     for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
-        passBTile<MODE, VARIANT, EXTRA>(p, cx, st, tid);
+        passBTile<MODE, VARIANT, EXTRA, CTHREADS_B>(p, cx, st, tid);
         mbarArrive(empty + s);   // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
     }
