@@ -79,6 +79,27 @@ static void syncStepSize(VVB200Shared &sh, const VVIntegrator &integrator) {
     }
 }
 
+// What makes two particles different for THIS plugin.  CudaContext::reorderAtoms only ever swaps molecules all of whose
+// ForceInfos call them identical [OMM-mem]; the reference registers none for its particle sets, which is why its
+// README (README.md:189-194) asks users to put whole classes of identical molecules into the Langevin / electrolyte /
+// image sets.  With this ForceInfo a molecule whose members carry different plugin roles is simply never swapped with
+// one that does not, so any subset is safe.  (The per-slot tables of the plan describe array slots; a swap of two
+// molecules that are identical in this sense leaves them valid.)
+class VVB200ForceInfo : public CudaForceInfo {
+public:
+    VVB200ForceInfo(int numParticles, const VVIntegrator &integrator) : role(numParticles, 0) {
+        for (int p : integrator.getParticlesLD()) role[p] |= 1;
+        for (const pair<int, int> &ip : integrator.getImagePairs()) {
+            role[ip.first] |= 2;       // image
+            role[ip.second] |= 4;      // has an image
+        }
+        for (int p : integrator.getParticlesElectrolyte()) role[p] += 8;     // multiplicity matters (field is added per entry)
+    }
+    bool areParticlesIdentical(int particle1, int particle2) override { return role[particle1] == role[particle2]; }
+private:
+    vector<int> role;
+};
+
 // Builds the plan from what VVIntegrator::initialize and the reference's Cuda*Kernel::initialize methods read
 // (VVIntegrator.cpp:123-151; CudaVVKernels.cpp:66-77, 483-594, 775-804, 884-891, 954-957, 1028-1031).
 static void createPlan(VVB200Shared &sh, CudaContext &cu, const System &system, const VVIntegrator &integrator,
@@ -160,6 +181,7 @@ static void createPlan(VVB200Shared &sh, CudaContext &cu, const System &system, 
     const int precision = cu.getUseDoublePrecision() ? VVB200_DOUBLE : cu.getUseMixedPrecision() ? VVB200_MIXED : VVB200_SINGLE;
     VVB200_CHECK(vvb200_plan_create(&s, &par, precision, &sh.plan));     // reference's exception texts on conflicts
     VVB200_CHECK(vvb200_plan_upload(sh.plan, cu.getCurrentStream()));
+    cu.addForce(new VVB200ForceInfo(n, integrator));     // owned by the context, like every ForceInfo
     sh.constrained = system.getNumConstraints() > 0 || virtualSites;
     sh.hasNH = !integrator.getParticlesNH().empty();
     sh.stepSize = par.step_size;

@@ -120,9 +120,21 @@ public:
         std::vector<class CudaContext *> contexts;
     };
 };
+// openmm/common/ComputeForceInfo.h + CudaForceInfo.h [OMM-mem]: what CudaContext::findMoleculeGroups consults before
+// it lets reorderAtoms swap two molecules
+class ComputeForceInfo {
+public:
+    virtual ~ComputeForceInfo() {}
+    virtual bool areParticlesIdentical(int particle1, int particle2) { return true; }
+    virtual int getNumParticleGroups() { return 0; }
+    virtual void getParticlesInGroup(int index, std::vector<int> &particles) {}
+    virtual bool areGroupsIdentical(int group1, int group2) { return true; }
+};
+class CudaForceInfo : public ComputeForceInfo {};
 class CudaContext {
 public:
     static const int ThreadBlockSize = 64;
+    void addForce(ComputeForceInfo *force);
     int getNumAtoms() const;
     int getPaddedNumAtoms() const;
     bool getUseDoublePrecision() const;
