@@ -116,6 +116,11 @@ struct KParams {
     const uint32_t *slotMeta;
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
+    // thermostat molecules cut across tiles (longer than a tile): fragment index per tile-local molecule, the cut
+    // molecules with their fragment lists, and the per-fragment sums (sum m v (3), sum m, sum m c) of this step
+    const int32_t *tileMolFrag, *splitMolId, *splitFragOffset, *splitFragList;
+    double *fragPartials;
+    int numSplit;
     void *posq, *corr, *velm;
     void *posDelta, *oldDelta;   // VAR_SCALE_DELTA only
     const long long *force;
@@ -144,6 +149,7 @@ enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2, VAR_SCALE_DELTA = 3
 #define MOLINFO_FIRST(w) ((w) & 0x7FF)
 #define MOLINFO_COUNT(w) (((w) >> 11) & 0x7FF)
 #define MOLINFO_SCATTERED(w) (((w) >> 31) & 1)
+#define MOLINFO_FRAGMENT(w) (((w) >> 30) & 1)     // part of a molecule that continues in a neighbouring tile
 
 __device__ __forceinline__ double cosPhase(double z, double invBoxZ) {
     // the reference's 8-digit pi literal and double-precision cos (cosineAccelerate.cu:9,26,70,83)
@@ -673,6 +679,8 @@ struct vvb200_device_state {
     int stagesA = 0, stagesB = 0, blocksPerSM = 0;   // 0: chosen per kernel from the shared-memory budget
     uint32_t *slotMeta = nullptr;
     int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
+    int32_t *tileMolFrag = nullptr, *splitMolId = nullptr, *splitFragOffset = nullptr, *splitFragList = nullptr;
+    double *fragPartials = nullptr;
     int2 *pairsLD = nullptr, *imagePairs = nullptr, *drudePairs = nullptr;
     // any-topology path
     int32_t *moleculesNH = nullptr, *normalNH = nullptr, *particleMolId = nullptr;
@@ -805,6 +813,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
                 const int m = p->tileMolList[k];
                 uint32_t w = (uint32_t) first[m] | ((uint32_t) cnt[m] << 11);
                 if (last[m] - first[m] + 1 != cnt[m]) w |= 1u << 31;
+                if (!p->tileMolFrag.empty() && p->tileMolFrag[k] >= 0) w |= 1u << 30;
                 molInfo[k] = (int32_t) w;
                 first[m] = last[m] = -1;
                 cnt[m] = 0;
@@ -831,6 +840,11 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     if ((rc = uploadVec(d, &d->slotMeta, metaPadded.data(), metaPadded.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->sortedByMol, p->sortedByMol.data(), p->sortedByMol.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->particlesInMolecules, p->particlesInMolecules.data(), p->particlesInMolecules.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->tileMolFrag, p->tileMolFrag.data(), p->tileMolFrag.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->splitMolId, p->splitMolId.data(), p->splitMolId.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->splitFragOffset, p->splitFragOffset.data(), p->splitFragOffset.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->splitFragList, p->splitFragList.data(), p->splitFragList.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->fragPartials, nullptr, p->splitFragList.size() * 5, st))) return rc;
     if ((rc = uploadVec(d, &d->ldSlot, p->ldSlot.data(), p->ldSlot.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->normalLD, p->normalLD.data(), p->normalLD.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->pairsLD, p->pairsLD.data(), p->pairsLD.size() / 2, st))) return rc;
@@ -921,6 +935,8 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
     k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
+    k.tileMolFrag = d->tileMolFrag; k.splitMolId = d->splitMolId; k.splitFragOffset = d->splitFragOffset;
+    k.splitFragList = d->splitFragList; k.fragPartials = d->fragPartials; k.numSplit = (int) p->splitMolId.size();
     k.posq = b->posq; k.corr = b->posq_correction; k.velm = b->velm; k.force = b->force;
     k.ldForce = d->ldForce; k.comV = d->comV; k.comCbar = d->comCbar;
     k.partials = d->partials; k.nhc = d->nhc; k.counter = d->counter; k.gridGen = d->counter + 1;

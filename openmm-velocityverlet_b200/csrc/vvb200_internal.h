@@ -79,6 +79,12 @@ struct vvb200_plan {
     std::vector<int32_t> tileMolList;           // global molecule id of each tile-local molecule
     std::vector<uint32_t> slotMeta;             // [N]
     std::vector<int32_t> ldSlot;                // [N] compact Langevin-force slot or -1 (only if LD)
+    // thermostat molecules longer than a tile are cut: each tile sums its fragment, the last block of pass A adds the
+    // fragments up (tile order) and finishes the molecule's centre of mass
+    std::vector<int32_t> tileMolFrag;           // per tile-local molecule: fragment index or -1
+    std::vector<int32_t> splitMolId;            // molecules that are cut, ascending
+    std::vector<int32_t> splitFragOffset;       // [numSplit+1] prefix into splitFragList
+    std::vector<int32_t> splitFragList;         // fragment indices of each cut molecule, in tile order
     std::vector<unsigned char> isNH, isLD, isImage;
 
     int64_t launches = 0;

@@ -390,9 +390,6 @@ static bool buildTiles(vvb200_plan *p) {
             cover[b + 1]--;
         }
     };
-    for (int m = 0; m < M; m++)
-        if (hi[m] >= 0)
-            protect(lo[m], hi[m]);
     std::vector<int32_t> partner(N, -1);
     std::vector<unsigned char> role(N, VVB200_ROLE_NONE);
     for (size_t k = 0; k < p->drudePairs.size(); k += 2) {
@@ -411,10 +408,25 @@ static bool buildTiles(vvb200_plan *p) {
             return false;
         }
     }
-    for (int i = 1; i <= N; i++)
-        cover[i] += cover[i - 1];
+    // Drude pairs are never cut; thermostat molecules are not cut either unless they are longer than a tile
+    // (splitLongerThan): those are summed fragment by fragment and finished by the last block of pass A
+    const std::vector<int32_t> pairCover = cover;
+    std::vector<unsigned char> isSplit(M, 0);
+    bool splitting = false;
+    auto buildCover = [&](int splitLongerThan) {
+        cover = pairCover;
+        std::fill(isSplit.begin(), isSplit.end(), 0);
+        for (int m = 0; m < M; m++)
+            if (hi[m] >= 0) {
+                if (hi[m] - lo[m] + 1 > splitLongerThan) isSplit[m] = 1;
+                else protect(lo[m], hi[m]);
+            }
+        for (int i = 1; i <= N; i++)
+            cover[i] += cover[i - 1];
+    };
+    buildCover(N + 1);
     // molBefore[i] = thermostat molecules whose first COM member lies below slot i (a tile owns the
-    // molecules that start inside it, because no cut separates a molecule's members)
+    // molecules that start inside it, plus at most one that continues from the tile before)
     std::vector<int32_t> molBefore(N + 1, 0);
     for (int m = 0; m < M; m++)
         if (hi[m] >= 0)
@@ -450,7 +462,7 @@ static bool buildTiles(vvb200_plan *p) {
         bool ok = true;
         while (s < N) {
             int32_t e = std::min(N, s + cap);
-            while (e > s + 1 && molBefore[e] - molBefore[s] > VVB200_TILE_MAX_MOLS)
+            while (e > s + 1 && molBefore[e] - molBefore[s] > VVB200_TILE_MAX_MOLS - (splitting ? 1 : 0))
                 e--;
             while (e > s && e < N && cover[e] != 0)
                 e--;
@@ -471,6 +483,11 @@ static bool buildTiles(vvb200_plan *p) {
             break;
         if (cap < VVB200_TILE_CAP) {     // a molecule longer than the small tile: fall back to full-size tiles
             cap = VVB200_TILE_CAP;
+            continue;
+        }
+        if (!splitting && useCOM && !(getenv("VVB200_SPLIT_MOLECULES") && atoi(getenv("VVB200_SPLIT_MOLECULES")) == 0)) {
+            splitting = true;            // polymers, proteins: cut the molecules that cannot fit a tile
+            buildCover(VVB200_TILE_CAP);
             continue;
         }
         p->tiledWhyNot = "a thermostat molecule or Drude pair spans more than one tile";
@@ -517,6 +534,27 @@ static bool buildTiles(vvb200_plan *p) {
         for (size_t k = base; k < p->tileMolList.size(); k++)
             localOf[p->tileMolList[k]] = -1;
         p->tileMolOffset[t + 1] = (int32_t) p->tileMolList.size();
+    }
+
+    // fragments of the cut molecules, numbered in tile order
+    p->tileMolFrag.assign(p->tileMolList.size(), -1);
+    p->splitMolId.clear();
+    p->splitFragOffset.assign(1, 0);
+    p->splitFragList.clear();
+    if (splitting) {
+        std::vector<std::vector<int32_t>> frags(M);
+        int32_t numFrag = 0;
+        for (size_t k = 0; k < p->tileMolList.size(); k++)
+            if (isSplit[p->tileMolList[k]]) {
+                p->tileMolFrag[k] = numFrag;
+                frags[p->tileMolList[k]].push_back(numFrag++);
+            }
+        for (int m = 0; m < M; m++)
+            if (isSplit[m] && !frags[m].empty()) {
+                p->splitMolId.push_back(m);
+                p->splitFragList.insert(p->splitFragList.end(), frags[m].begin(), frags[m].end());
+                p->splitFragOffset.push_back((int32_t) p->splitFragList.size());
+            }
     }
 
     // compact Langevin-force slots: normal i -> i, pair k -> nNormal + 2k (Drude), +1 (parent):

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
         const bool last = blockReduceAndTicket<NR>(p, sm, acc, tid);
         traceMark(4);
         if (last) {
-            lastBlockFinish<NR>(p, sm, cosine, tid, &nhcS);
+            lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS);
             consumerBarrier();
             nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
             consumerBarrier();        // the release below is cumulative over what the barrier ordered before it
@@ -166,6 +166,26 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
     }
     __syncthreads();
     traceMark(5);
+
+    // molecules cut across tiles were finished by the last block: fetch their velocities into the stages
+    if (p.numSplit > 0 && useCOM) {
+        for (int j = 0; j < T; j++) {
+            const int tile = blockIdx.x + j * gridDim.x;
+            if (tile >= p.numTiles) break;
+            Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * j);
+            const int m0 = st.desc[2], nMol = st.desc[3], molFirst = st.desc[4], ml0 = m0 - (m0 & ~3);
+            if (tid < nMol && MOLINFO_FRAGMENT((uint32_t) st.molInfo[ml0 + tid])) {
+                const int mol = molFirst >= 0 ? molFirst + tid : p.tileMolList[m0 + tid];
+                const double *src = reinterpret_cast<const double *>(reinterpret_cast<const mixed4 *>(p.comV) + mol);
+                mixed4 V;
+                if (sizeof(mixed) == 8) { V.x = (mixed) __ldcg(src); V.y = (mixed) __ldcg(src + 1); V.z = (mixed) __ldcg(src + 2); V.w = (mixed) __ldcg(src + 3); }
+                else { const float *sf = reinterpret_cast<const float *>(src); V.x = (mixed) __ldcg(sf); V.y = (mixed) __ldcg(sf + 1); V.z = (mixed) __ldcg(sf + 2); V.w = (mixed) __ldcg(sf + 3); }
+                st.comV[tid] = V;
+                if (EXTRA && p.cosine) st.cbar[tid] = __ldcg(reinterpret_cast<const mixed *>(p.comCbar) + mol);
+            }
+        }
+        __syncthreads();
+    }
 
     // ===== pass B from the same stages =====
     BCtx<MODE> cb = makeBCtx<MODE>(p, EXTRA);

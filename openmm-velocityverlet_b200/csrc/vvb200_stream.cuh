@@ -314,7 +314,11 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
                 comMass += __shfl_xor_sync(0xffffffffu, comMass, off);
                 if (EXTRA) sc += __shfl_xor_sync(0xffffffffu, sc, off);
             }
-            if (active && sub == 0) {
+            if (active && sub == 0 && MOLINFO_FRAGMENT(info)) {
+                // part of a molecule that is longer than a tile: leave the sums for the last block (lastBlockFinish)
+                double *fp = p.fragPartials + 5 * (size_t) p.tileMolFrag[m0 + j];
+                fp[0] = (double) sx; fp[1] = (double) sy; fp[2] = (double) sz; fp[3] = (double) comMass; fp[4] = (double) sc;
+            } else if (active && sub == 0) {
                 mixed4 V;
                 V.w = vv_recip(comMass);
                 V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
@@ -414,9 +418,11 @@ __device__ __forceinline__ bool blockReduceAndTicket(const KParams &p, Scratch &
 // ---- the last block sums the per-block partials block-major in a fixed order and advances the NH chains ---------
 // `work`: the thermostat state to advance -- p.nhc itself, or a shared-memory copy the caller prefetched and writes
 // back afterwards (resident kernel: saves the chain's serial L2 round trips).
-template <int NR, class Scratch>
+template <int MODE, int NR, class Scratch>
 __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, const bool cosine, const int tid,
                                                 NhcDevice *work = nullptr) {
+    typedef typename Prec<MODE>::mixed mixed;
+    typedef typename Prec<MODE>::mixed4 mixed4;
     if (!work) work = p.nhc;
     const int lane = tid & 31, warp = tid >> 5;
     __threadfence();
@@ -428,6 +434,31 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
 #pragma unroll
         for (int k = 0; k < NR; k++)
             tot[k] += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
+    }
+    // molecules cut across tiles: add their fragments up in tile order, finish the centre of mass the way phase 2 does
+    // for whole molecules (drudeNoseHoover.cu:11-30, 91-97) and move M|V|^2 from the atom group to the molecular group
+    for (int k = tid; k < (p.kickOnly ? 0 : p.numSplit); k += CTHREADS) {
+        mixed sx = 0, sy = 0, sz = 0, comMass = 0, sc = 0;
+        for (int f = p.splitFragOffset[k]; f < p.splitFragOffset[k + 1]; f++) {
+            const double *fp = p.fragPartials + 5 * (size_t) p.splitFragList[f];
+            sx += (mixed) __ldcg(fp); sy += (mixed) __ldcg(fp + 1); sz += (mixed) __ldcg(fp + 2);
+            comMass += (mixed) __ldcg(fp + 3); sc += (mixed) __ldcg(fp + 4);
+        }
+        const int mol = p.splitMolId[k];
+        mixed4 V;
+        V.w = vv_recip(comMass);
+        V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
+        reinterpret_cast<mixed4 *>(p.comV)[mol] = V;
+        const mixed mv2 = (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
+        tot[1] += (double) mv2;
+        tot[0] -= (double) mv2;
+        if (NR > 3 && cosine) {
+            const mixed cb = sc * V.w;
+            reinterpret_cast<mixed *>(p.comCbar)[mol] = cb;
+            const mixed b = comMass * V.x * cb, c = comMass * cb * cb;
+            tot[NR > 3 ? 5 : 0] += (double) b; tot[NR > 3 ? 4 : 0] -= (double) b;
+            tot[NR > 3 ? 8 : 0] += (double) c; tot[NR > 3 ? 7 : 0] -= (double) c;
+        }
     }
 #pragma unroll
     for (int k = 0; k < NR; k++) {
@@ -558,11 +589,11 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
     if (!blockReduceAndTicket<NR>(p, sm, acc, tid))
         return;
     if (p.fuseNHC) {
-        lastBlockFinish<NR>(p, sm, cosine, tid, &nhcS);
+        lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS);
         consumerBarrier();
         nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
     } else {
-        lastBlockFinish<NR>(p, sm, cosine, tid);
+        lastBlockFinish<MODE, NR>(p, sm, cosine, tid);
     }
 }
 

@@ -190,13 +190,32 @@ def make_nonpolar_box(n_molecules=512, atoms_per_molecule=8, has_cmm=True):
     return spec.finalize(mol_id=mol_id)
 
 
-def make_polymer(n_chains=3, chain_len=700, n_solvent=40, has_cmm=False):
+def make_polymer(n_chains=3, chain_len=700, n_solvent=40, has_cmm=False, adjacent=False):
     """Polarizable polymer chains under NH: each chain is ONE molecule of 2*chain_len particles (backbone atom +
-    its Drude, parents listed first then all Drudes, so partners sit chain_len slots apart) -- neither the molecule nor
-    the pairs fit a 512-slot tile.  Plus a few small solvent molecules.  Exercises the any-topology path."""
+    its Drude).  adjacent=False: parents listed first then all Drudes, so partners sit chain_len slots apart --
+    neither the molecule nor the pairs fit a tile: the any-topology path.  adjacent=True: every Drude follows its
+    parent (what OpenMM's Drude builders produce), with one hydrogen per second backbone atom -- the molecule is longer
+    than a tile but can be cut between pairs: the fused path with cross-tile centres of mass.  Plus a few small
+    solvent molecules."""
     masses, bonds, pairs = [], [], []
     base = 0
     for _ in range(n_chains):
+        if adjacent:
+            prev, i = -1, base
+            for k in range(chain_len):
+                masses.extend([13.607 if k % 2 == 0 else 11.611, 0.4])
+                pairs.append((i + 1, i))
+                bonds.append((i, i + 1))
+                if prev >= 0:
+                    bonds.append((prev, i))
+                prev = i
+                i += 2
+                if k % 2 == 1:
+                    masses.append(1.008)
+                    bonds.append((prev, i))
+                    i += 1
+            base = i
+            continue
         for k in range(chain_len):
             masses.append(13.607 if k % 2 == 0 else 11.611)
             if k:
@@ -211,7 +230,7 @@ def make_polymer(n_chains=3, chain_len=700, n_solvent=40, has_cmm=False):
         bonds.extend([(base, base + 1), (base, base + 2)])
         base += 3
     spec = SystemSpec(n=base, masses=np.array(masses), bonds=np.array(bonds, np.int32), drude_pairs=np.array(pairs, np.int32),
-                      has_cmm=has_cmm, name=f"polymer_{n_chains}x{chain_len}")
+                      has_cmm=has_cmm, name=f"polymer_{n_chains}x{chain_len}{'_adjacent' if adjacent else ''}")
     return spec.finalize()
 
 

@@ -17,9 +17,11 @@ P = vv.Params
 bulk = vv.make_bulk_ionic_liquid(40)
 edl = vv.make_edl(n_ion_pairs=12, n_electrode=120, electrode_molecules=3)
 poly = vv.make_polymer(1, 600, 10)
+poly_adj = vv.make_polymer(2, 500, 10, adjacent=True)       # molecules cut across tiles on the fused path
 cases = [(bulk, P(max_drude_distance=0.02), {}), (bulk, P(max_drude_distance=0.02, cos_acceleration=0.02), dict(cos=True)),
          (edl, P(max_drude_distance=0.02, mirror_location=1.2, electric_field=0.25 * EV), dict(n_random=4 * 122 * 4, mirror=1.2)),
-         (poly, P(max_drude_distance=0.02), {})]
+         (poly, P(max_drude_distance=0.02), {}), (poly_adj, P(max_drude_distance=0.02), {}),
+         (poly_adj, P(max_drude_distance=0.02, cos_acceleration=0.02), dict(cos=True))]
 for spec, params, kw in cases:
     for middle in (True, False):
         for mode in ("mixed", "single", "double"):

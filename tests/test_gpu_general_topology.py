@@ -112,3 +112,69 @@ def test_general_equals_tiled(vv, vo):
     n = spec.n
     assert rel_err(hb.velm[:n, :3], ha.velm[:n, :3]) <= 1e-10 and rel_err(hb.positions()[:n], ha.positions()[:n]) <= 1e-12
     assert general.launch_count > tiled.launch_count
+
+
+# ---- thermostat molecules longer than a tile, Drudes next to their parents: the FUSED path cuts the molecule, every tile
+#      sums its fragment and the last block of pass A finishes the centre of mass (csrc/vvb200_stream.cuh) --------------
+@pytest.mark.parametrize("middle", [True, False])
+@pytest.mark.parametrize("precision", ["mixed", "double"])
+def test_long_molecules_run_on_the_fused_path(vv, vo, precision, middle):
+    spec = vv.make_polymer(3, 700, 40, has_cmm=True, adjacent=True)      # 3 chains of 1,750 particles + 40 waters
+    params = dataclasses.replace(vv.Params(max_drude_distance=0.02).resolved_for(spec), use_middle_scheme=middle)
+    plan, _ = run(vv, vo, spec, params, precision, 3, expect_tiled=True)
+    assert plan.num_temp_groups == 3
+    assert np.max(np.diff(plan.int_array("tileStart"))) <= 512 < 1750
+
+
+def test_long_molecules_cosine_and_single(vv, vo):
+    spec = vv.make_polymer(2, 900, 30, adjacent=True)
+    params = vv.Params(max_drude_distance=0.02, cos_acceleration=0.02).resolved_for(spec)
+    host0 = vv.make_state(spec, "mixed")
+    run(vv, vo, spec, params, "mixed", 3, inv_box_z=1.0 / host0.box[2], expect_tiled=True)
+    # single precision: tolerance of the single-precision parity tests
+    from conftest import rms_err
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "single")
+    plan = vv.Plan(spec, params, "single").upload()
+    assert plan.tiled
+    bufs = vv.DeviceBuffers(host)
+    plan.step(bufs, steps=3)
+    got, want = bufs.to_host(), host.copy()
+    vo.Oracle(spec, params, "single", literal=False).step(want, steps=3)
+    n = spec.n
+    assert rms_err(got.velm[:n, :3], want.velm[:n, :3]) <= 1e-4 and rms_err(got.positions()[:n], want.positions()[:n]) <= 1e-4
+
+
+def test_long_molecules_fused_equals_any_topology_path(vv, vo, monkeypatch):
+    """a polymer melt of 203k particles (streaming kernels; 40 chains of 5,000 particles cut into ~10 fragments each):
+    the fused path with cross-tile centres of mass against the gather kernels of the any-topology path"""
+    import torch
+    spec = vv.make_polymer(40, 2000, 1000, adjacent=True)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", force_sigma=1.0)
+    fused = vv.Plan(spec, params, "mixed").upload()
+    monkeypatch.setenv("VVB200_SPLIT_MOLECULES", "0")
+    general = vv.Plan(spec, params, "mixed").upload()
+    assert fused.tiled and not general.tiled
+    a, b = vv.DeviceBuffers(host), vv.DeviceBuffers(host)
+    fused.step(a, steps=4)
+    general.step(b, steps=4)
+    ha, hb = a.to_host(), b.to_host()
+    n = spec.n
+    assert rel_err(ha.velm[:n, :3], hb.velm[:n, :3]) <= 1e-10 and rel_err(ha.positions()[:n], hb.positions()[:n]) <= 1e-12
+    sa, sb = fused.thermostat_state(), general.thermostat_state()
+    assert rel_err(sa["ke2"], sb["ke2"]) <= 1e-12 and rel_err(sa["vscale"], sb["vscale"]) <= 1e-12
+    assert rel_err(fused.com_velocities()[:, :3], general.com_velocities()[:, :3]) <= 1e-9
+    assert fused.launch_count < general.launch_count
+    # and it is what makes the difference for such systems: time both
+    st = torch.cuda.current_stream()
+    out = []
+    for plan, bufs in ((fused, a), (general, b)):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        plan.step(bufs, steps=50)
+        e1.record(st)
+        torch.cuda.synchronize()
+        out.append(1e3 * e0.elapsed_time(e1) / 50)
+    print(f"polymer melt {n} particles: fused {out[0]:.1f} us/step, any-topology path {out[1]:.1f} us/step")
