@@ -116,6 +116,12 @@ struct KParams {
     const uint32_t *slotMeta;
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
+    // Langevin force evaluated inside the kick (middle scheme): OpenMM's N(0,1) buffer, the index of this step's first
+    // number, the coefficients of CudaVVKernels.cpp:835-839 and the number of unpaired Langevin particles
+    const float4 *random;
+    unsigned int randomIndex;
+    int ldInline, nNormalLD;
+    double ldDrag, ldRand, ldDragDrude, ldRandDrude;
     // thermostat molecules cut across tiles (longer than a tile): fragment index per tile-local molecule, the cut
     // molecules with their fragment lists, and the per-fragment sums (sum m v (3), sum m, sum m c) of this step
     const int32_t *tileMolFrag, *splitMolId, *splitFragOffset, *splitFragList;
@@ -926,6 +932,8 @@ static int checkStepArgs(const vvb200_plan *p, const vvb200_buffers *b, const ch
     return VVB200_OK;
 }
 
+static int envInt(const char *name, int dflt);
+
 static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a) {
     const vvb200_device_state *d = p->dev;
     KParams k;
@@ -954,6 +962,16 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.fuseNHC = 1;
     k.cosine = p->par.cos_acceleration != 0;
     k.kickOnly = p->tiled ? 0 : 1;
+    // Langevin force inside the kick: middle scheme on the tiled path (pairs are never cut there)
+    static const int ldInlineEnv = envInt("VVB200_LD_INLINE", 1);
+    k.ldInline = ldInlineEnv && p->tiled && p->par.use_middle_scheme && !p->particlesLD.empty() && b->random != nullptr;
+    k.random = (const float4 *) b->random;
+    k.randomIndex = a ? a->random_index : 0;
+    k.nNormalLD = (int) p->normalLD.size();
+    k.ldDrag = p->par.friction;                                                           // CudaVVKernels.cpp:835-839
+    k.ldDragDrude = p->par.drude_friction;
+    k.ldRand = std::sqrt(2.0 * BOLTZ_D * p->par.temperature * p->par.friction / p->par.step_size);
+    k.ldRandDrude = std::sqrt(2.0 * BOLTZ_D * p->par.drude_temperature * p->par.drude_friction / p->par.step_size);
     return k;
 }
 
@@ -1157,6 +1175,8 @@ static int tryResident(vvb200_plan *p, KParams k, bool reduce, cudaStream_t st, 
 
 static int launchLangevin(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, cudaStream_t st) {
     vvb200_device_state *d = p->dev;
+    if (makeParams(p, b, a).ldInline)
+        return VVB200_OK;        // middle scheme on the tiled path: evaluated inside the kick (langevinForceInline)
     const int nNormal = (int) p->normalLD.size(), nPairs = (int) p->pairsLD.size() / 2;
     const int work = std::max(nNormal, nPairs);
     if (work == 0)

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             uint32_t meta[ITEMS];
             passAPhase1<MODE, KICK, EXTRA, true>(p, ca, st, pub, vel, meta, acc, tid);
             consumerBarrier();
-            passAPhase23<MODE, EXTRA, true>(p, ca, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst);
+            passAPhase23<MODE, EXTRA, true, Stage, KICK>(p, ca, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst);
             buf ^= 1;
         }
     }

@@ -160,6 +160,60 @@ template <int MODE, int KICK> __device__ __forceinline__ ACtx<MODE> makeACtx(con
     return c;
 }
 
+// addExtraForceDrudeLangevin (drudeLangevin.cu:2-59) for ONE particle, evaluated inside the kick instead of by a
+// launch of its own: same expressions as langevin_force_kernel (which the velocity-Verlet scheme still uses, because
+// its first half re-applies the force of the half before).  `v` is this particle's pre-kick velocity; a pair member
+// reads its partner's from the stage (pairs are never cut by a tile boundary).
+template <int MODE, class Stage>
+__device__ __forceinline__ void langevinForceInline(const KParams &p, const Stage &st, const int sl, const int slot,
+                                                    const uint32_t mw, const typename Prec<MODE>::mixed4 v,
+                                                    typename Prec<MODE>::real &ex, typename Prec<MODE>::real &ey,
+                                                    typename Prec<MODE>::real &ez) {
+    typedef typename Prec<MODE>::real real;
+    typedef typename Prec<MODE>::mixed mixed;
+    typedef typename Prec<MODE>::mixed4 mixed4;
+    const mixed dragFactor = (mixed) p.ldDrag, randFactor = (mixed) p.ldRand;
+    const uint32_t role = (mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK;
+    if (slot < p.nNormalLD) {
+        ex = ey = ez = 0;
+        if (v.w != 0) {
+            const mixed mass = vv_recip(v.w);
+            const mixed sqrtMass = vv_sqrt<MODE, mixed>(mass);
+            const float4 r = __ldg(p.random + p.randomIndex + slot);
+            ex += (-dragFactor * mass * v.x + randFactor * sqrtMass * r.x);
+            ey += (-dragFactor * mass * v.y + randFactor * sqrtMass * r.y);
+            ez += (-dragFactor * mass * v.z + randFactor * sqrtMass * r.z);
+        }
+        return;
+    }
+    const mixed dragFactorDrude = (mixed) p.ldDragDrude, randFactorDrude = (mixed) p.ldRandDrude;
+    const bool selfIsDrude = role == VVB200_ROLE_DRUDE;
+    const int psl = sl + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+    const mixed4 vp = st.velm[psl];
+    const mixed4 v1 = selfIsDrude ? v : vp, v2 = selfIsDrude ? vp : v;      // (Drude, parent) like pairsLD
+    const int pairSlot = selfIsDrude ? slot : slot - 1;                     // slots: nNormal + 2k (Drude), + 1 (parent)
+    const mixed mass1 = vv_recip(v1.w), mass2 = vv_recip(v2.w);
+    const mixed totMass = mass1 + mass2;
+    const mixed sqrtTotMass = vv_sqrt<MODE, mixed>(totMass);
+    const mixed redMass = vv_recip((mass1 + mass2) * v1.w * v2.w);
+    const mixed sqrtRedMass = vv_sqrt<MODE, mixed>(redMass);
+    const mixed invTotMass = vv_recip(totMass);
+    const mixed m1f = invTotMass * mass1, m2f = invTotMass * mass2;
+    const float4 r1 = __ldg(p.random + p.randomIndex + pairSlot), r2 = __ldg(p.random + p.randomIndex + pairSlot + 1);
+    const mixed cm[3] = {v1.x * m1f + v2.x * m2f, v1.y * m1f + v2.y * m2f, v1.z * m1f + v2.z * m2f};
+    const mixed rel[3] = {v2.x - v1.x, v2.y - v1.y, v2.z - v1.z};
+    const float ra[3] = {r1.x, r1.y, r1.z}, rb[3] = {r2.x, r2.y, r2.z};
+    const real f1 = (real) m1f, f2 = (real) m2f;
+    real out[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const real cmForce = (real) (-dragFactor * totMass * cm[d] + randFactor * sqrtTotMass * ra[d]);
+        const real relForce = (real) (-dragFactorDrude * redMass * rel[d] + randFactorDrude * sqrtRedMass * rb[d]);
+        out[d] = selfIsDrude ? (real) 0 + (f1 * cmForce - relForce) : (real) 0 + (f2 * cmForce + relForce);
+    }
+    ex = out[0]; ey = out[1]; ez = out[2];
+}
+
 // ---- phase 1: extra forces, kick, store; publish v' and mass ----------------------------------------
 template <int MODE, int KICK, bool EXTRA, bool RESIDENT, class Stage>
 __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &cx, Stage &st, PublishedA<MODE, EXTRA> &pub,
@@ -204,8 +258,12 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
                     real ex = 0, ey = 0, ez = 0;
                     if (p.extraForces) {
                         if (p.hasLD && (meta[it] & VVB200_META_LD)) {
-                            const real3 f = ldForce[p.ldSlot[idx]];
-                            ex = f.x; ey = f.y; ez = f.z;
+                            if (KICK == KICK_MIDDLE && p.ldInline) {
+                                langevinForceInline<MODE>(p, st, sl, p.ldSlot[idx], meta[it], v, ex, ey, ez);
+                            } else {
+                                const real3 f = ldForce[p.ldSlot[idx]];
+                                ex = f.x; ey = f.y; ez = f.z;
+                            }
                         }
                         if (p.hasField) {
                             const int cnt = (meta[it] >> VVB200_META_ELEC_SHIFT) & VVB200_META_ELEC_MASK;
@@ -230,8 +288,9 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
                     v.y += fscale * v.w * fy;
                     v.z += fscale * v.w * fz;
                 }
-                if constexpr (RESIDENT) st.velm[sl] = v;      // stays on chip for pass B
-                else st_stream(velm + idx, v);
+                // resident kernel: the kicked velocity stays on chip for pass B, but it goes back into the stage only
+                // after the block barrier (passAPhase23): a Langevin pair partner may still need the pre-kick value
+                if constexpr (!RESIDENT) st_stream(velm + idx, v);
             }
             const mixed mass = v.w != 0 ? vv_recip(v.w) : (mixed) 0;
             vel[it] = v;
@@ -260,7 +319,7 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
 }
 
 // ---- phases 2 and 3 (after a block barrier): molecular COM velocities, then the Drude pairs -----------
-template <int MODE, bool EXTRA, bool RESIDENT, class Stage>
+template <int MODE, bool EXTRA, bool RESIDENT, class Stage, int KICK = KICK_NONE>
 __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> &cx, Stage &st, PublishedA<MODE, EXTRA> &pub,
                                              const typename Prec<MODE>::mixed4 (&vel)[ITEMS], const uint32_t (&meta)[ITEMS],
                                              typename Prec<MODE>::mixed (&acc)[EXTRA ? VVB200_NRED : 3], const int tid,
@@ -272,6 +331,17 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
     mixed *comCbar = reinterpret_cast<mixed *>(p.comCbar);
     const bool cosine = cx.cosine;
     (void) st;
+    if constexpr (RESIDENT && KICK != KICK_NONE) {
+        // the kicked velocities into the stage (each thread its own slots; read again after the grid barrier)
+        const int sl0 = t0 - (t0 & ~3);
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * CTHREADS + tid;
+            if (t0 + loc < t1 && vel[it].w != 0) {
+                st.velm[sl0 + loc].x = vel[it].x; st.velm[sl0 + loc].y = vel[it].y; st.velm[sl0 + loc].z = vel[it].z;
+            }
+        }
+    }
     // ---- phase 2: molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30): COM_LANES lanes per
     //      molecule stride over its particles, then a butterfly over the lane group (fixed order) ----
     if (nMol > 0) {
