@@ -116,6 +116,10 @@ struct KParams {
     const uint32_t *slotMeta;
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
+    // image update fused into pass B: image index per parent, mirror plane
+    const int32_t *imageOf;
+    double mirror;
+    int imageFused;
     // Langevin force evaluated inside the kick (middle scheme): OpenMM's N(0,1) buffer, the index of this step's first
     // number, the coefficients of CudaVVKernels.cpp:835-839 and the number of unpaired Langevin particles
     const float4 *random;
@@ -685,6 +689,7 @@ struct vvb200_device_state {
     int stagesA = 0, stagesB = 0, blocksPerSM = 0;   // 0: chosen per kernel from the shared-memory budget
     uint32_t *slotMeta = nullptr;
     int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
+    int32_t *imageOf = nullptr;
     int32_t *tileMolFrag = nullptr, *splitMolId = nullptr, *splitFragOffset = nullptr, *splitFragList = nullptr;
     double *fragPartials = nullptr;
     int2 *pairsLD = nullptr, *imagePairs = nullptr, *drudePairs = nullptr;
@@ -846,6 +851,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     if ((rc = uploadVec(d, &d->slotMeta, metaPadded.data(), metaPadded.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->sortedByMol, p->sortedByMol.data(), p->sortedByMol.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->particlesInMolecules, p->particlesInMolecules.data(), p->particlesInMolecules.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->imageOf, p->imageOf.data(), p->imageOf.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolFrag, p->tileMolFrag.data(), p->tileMolFrag.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->splitMolId, p->splitMolId.data(), p->splitMolId.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->splitFragOffset, p->splitFragOffset.data(), p->splitFragOffset.size(), st))) return rc;
@@ -962,6 +968,10 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.fuseNHC = 1;
     k.cosine = p->par.cos_acceleration != 0;
     k.kickOnly = p->tiled ? 0 : 1;
+    static const int imageFusedEnv = envInt("VVB200_IMAGE_FUSED", 1);
+    k.imageFused = imageFusedEnv && p->tiled && !p->imageOf.empty();
+    k.imageOf = d->imageOf;
+    k.mirror = p->par.mirror_location;
     // Langevin force inside the kick: middle scheme on the tiled path (pairs are never cut there)
     static const int ldInlineEnv = envInt("VVB200_LD_INLINE", 1);
     k.ldInline = ldInlineEnv && p->tiled && p->par.use_middle_scheme && !p->particlesLD.empty() && b->random != nullptr;
@@ -1428,7 +1438,7 @@ extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffer
     CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, p->par.cos_acceleration != 0, k, p->dev->numSM, st)));
     p->launches++;
     profMark(p->dev, 3, st);
-    return vvb200_update_image_positions(p, b, stream);
+    return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
 }
 
 extern "C" int vvb200_peer_export(vvb200_plan *p, void *handleOut64) {
@@ -1512,7 +1522,7 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
         profMark(p->dev, 1, st);
         profMark(p->dev, 2, st);
         profMark(p->dev, 3, st);
-        return vvb200_update_image_positions(p, b, stream);
+        return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
     }
     CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
@@ -1521,7 +1531,7 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
     CUDA_TRY((dispatchB<VAR_MIDDLE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
     profMark(p->dev, 3, st);
-    return vvb200_update_image_positions(p, b, stream);
+    return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
 }
 
 extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
@@ -1549,14 +1559,14 @@ extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, con
     bool resident = false;
     if ((rc = tryResident<KICK_NONE, VAR_VV_FIRST>(p, k, hasNH(p), st, &resident))) return rc;
     if (resident)
-        return vvb200_update_image_positions(p, b, stream);
+        return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
     if (hasNH(p)) {
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
     }
     CUDA_TRY((dispatchB<VAR_VV_FIRST>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
-    return vvb200_update_image_positions(p, b, stream);
+    return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
 }
 
 extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {

@@ -14,6 +14,7 @@
 //              a molecular centre of mass)
 //  bits 11-13  how many times the particle appears in the electrolyte list (duplicates add twice,
 //              CudaVVKernels.cpp:954-957 / electricField.cu:7-11)
+//  bit  14     has an image particle that pass B mirrors along (fused image update)
 //  bit  16     member of the Nose-Hoover set (VVIntegrator::isParticleNH)
 //  bits 17-18  Drude pair role: 0 none, 1 Drude (pair.x), 2 parent (pair.y)
 //  bit  19     Langevin particle (has an entry in ldSlot[])
@@ -22,6 +23,7 @@
 #define VVB200_META_MOL_NONE 0x7FFu
 #define VVB200_META_ELEC_SHIFT 11
 #define VVB200_META_ELEC_MASK 0x7u
+#define VVB200_META_HAS_IMAGE (1u << 14)    // parent of an image particle (imageOf[] holds the image's index)
 #define VVB200_META_NH (1u << 16)
 #define VVB200_META_ROLE_SHIFT 17
 #define VVB200_META_ROLE_MASK 0x3u
@@ -81,6 +83,7 @@ struct vvb200_plan {
     std::vector<int32_t> ldSlot;                // [N] compact Langevin-force slot or -1 (only if LD)
     // thermostat molecules longer than a tile are cut: each tile sums its fragment, the last block of pass A adds the
     // fragments up (tile order) and finishes the molecule's centre of mass
+    std::vector<int32_t> imageOf;               // [N] index of the particle's image or -1; empty unless the image update is fused
     std::vector<int32_t> tileMolFrag;           // per tile-local molecule: fragment index or -1
     std::vector<int32_t> splitMolId;            // molecules that are cut, ascending
     std::vector<int32_t> splitFragOffset;       // [numSplit+1] prefix into splitFragList

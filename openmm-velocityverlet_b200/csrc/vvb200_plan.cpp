@@ -536,6 +536,25 @@ static bool buildTiles(vvb200_plan *p) {
         p->tileMolOffset[t + 1] = (int32_t) p->tileMolList.size();
     }
 
+    // Image update fused into pass B: possible when every parent has exactly one image, no image is itself a parent and
+    // images are massless particles outside both thermostats (their own thread then writes nothing)
+    p->imageOf.clear();
+    if (!p->imagePairs.empty()) {
+        std::vector<int32_t> imageOf(N, -1);
+        bool ok = true;
+        for (size_t k = 0; k < p->imagePairs.size() && ok; k += 2) {
+            const int32_t img = p->imagePairs[k], parent = p->imagePairs[k + 1];
+            ok = imageOf[parent] < 0 && !p->isImage[parent] && p->masses[img] == 0.0 && !p->isNH[img] && !p->isLD[img] &&
+                 role[img] == VVB200_ROLE_NONE;
+            imageOf[parent] = img;
+        }
+        if (ok) {
+            p->imageOf.swap(imageOf);
+            for (int i = 0; i < N; i++)
+                if (p->imageOf[i] >= 0) p->slotMeta[i] |= VVB200_META_HAS_IMAGE;
+        }
+    }
+
     // fragments of the cut molecules, numbered in tile order
     p->tileMolFrag.assign(p->tileMolList.size(), -1);
     p->splitMolId.clear();

@@ -1056,10 +1056,9 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
             mixed4 o; o.x = vs[0]; o.y = vs[1]; o.z = vs[2]; o.w = ws;
             st_stream(velm + idx, o);
         }
+        real4 o = pq, oc = cs;      // this particle's position as the arrays hold it after this step
         if (POS && writePos) {
-            real4 o;
             if (P::kMixed) {
-                real4 oc;
                 splitPos<MODE>(xs[0], o.x, oc.x);
                 splitPos<MODE>(xs[1], o.y, oc.y);
                 splitPos<MODE>(xs[2], o.z, oc.z);
@@ -1070,6 +1069,26 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
             } else {
                 o.x = (real) xs[0]; o.y = (real) xs[1]; o.z = (real) xs[2]; o.w = pq.w;
                 st_stream(posq + idx, o);
+            }
+        }
+        // updateImagePositions (imageCharge.cu:2-27) by the PARENT's thread: x, y copied, z mirrored, from the position
+        // just written; the image's charge and correction .w are left alone (three scalar stores each).  The image
+        // particle itself is massless and outside the thermostat: its own thread writes nothing.
+        if (POS && p.imageFused && (mw & VVB200_META_HAS_IMAGE)) {
+            const int img = p.imageOf[idx];
+            real *ip = reinterpret_cast<real *>(posq + img);
+            ip[0] = o.x;
+            ip[1] = o.y;
+            if (P::kMixed) {
+                real *ic = reinterpret_cast<real *>(corr + img);
+                ic[0] = oc.x;
+                ic[1] = oc.y;
+                mixed z = (mixed) o.z + (mixed) oc.z;
+                z = (mixed) p.mirror * 2 - z;
+                ip[2] = (real) z;
+                ic[2] = (real) (z - (real) z);
+            } else {
+                ip[2] = 2 * (mixed) p.mirror - o.z;
             }
         }
     }

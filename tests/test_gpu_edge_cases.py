@@ -286,3 +286,25 @@ def test_checkpoint_resumes_bitwise(vv, vo):
     with pytest.raises(vv.VVB200Error) as e:
         other.checkpoint_load(blob)
     assert e.value.code == 2
+
+
+def test_edl_step_is_one_launch(vv, vo, step_path):
+    """BASELINE config 3 (electrode + electrolyte: Langevin subset, external field, image charges): the Langevin force is
+    evaluated inside the kick and the image particles are mirrored by their parents' threads, so the whole step is one
+    launch when resident (two streaming passes otherwise); the reference needs 14"""
+    spec = vv.make_edl(n_ion_pairs=64, n_electrode=624, electrode_molecules=4)
+    params = vv.Params(max_drude_distance=0.02, mirror_location=2.0, electric_field=0.25 * 1.60217662e-22).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", n_random=8 * 626, mirror=2.0)
+    plan = vv.Plan(spec, params, "mixed").upload()
+    bufs = vv.DeviceBuffers(host)
+    ri = plan.step(bufs, steps=4)
+    assert ri == 4 * plan.random_request
+    assert plan.launch_count == (4 if step_path == "resident" else 8)
+    got, want = bufs.to_host(), host.copy()
+    vo.Oracle(spec, params, "mixed", literal=False).step(want, steps=4)
+    n = spec.n
+    assert rel_err(got.velm[:n, :3], want.velm[:n, :3]) <= TIGHT_HARDWALL["mixed"]
+    assert rel_err(got.positions()[:n], want.positions()[:n]) <= TIGHT_HARDWALL["mixed"]
+    img = spec.image_pairs[:, 0]
+    assert np.array_equal(got.posq[img, 3], host.posq[img, 3])            # the images keep their own charges
+    assert np.array_equal(got.posq[img, :2], got.posq[spec.image_pairs[:, 1], :2])   # x, y copied bit for bit
