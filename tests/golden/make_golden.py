@@ -37,12 +37,23 @@ def cases():
     edl = vv.make_edl(n_ion_pairs=6, n_electrode=60, electrode_molecules=3)
     yield "edl_langevin_field_image_mixed", edl, P(max_drude_distance=0.02, mirror_location=1.0,
                                                    electric_field=0.25 * EV).resolved_for(edl), "mixed", 3, dict(mirror=1.0, n_random=4 * 62)
+    # added later (python tests/golden/make_golden.py polymer edl_vv bulk_tgnh_middle_double): a thermostat molecule
+    # longer than a tile (the fused path cuts it and sums the fragments), the EDL system under the VV scheme, double
+    poly = vv.make_polymer(1, 330, 6, has_cmm=True, adjacent=True)
+    yield "polymer_cut_molecule_mixed", poly, P(max_drude_distance=0.02).resolved_for(poly), "mixed", 3, {}
+    yield "polymer_cut_molecule_cosine_mixed", poly, P(max_drude_distance=0.02, cos_acceleration=0.02).resolved_for(poly), "mixed", 3, dict(cos=True)
+    yield "edl_vv_mixed", edl, dataclasses.replace(P(max_drude_distance=0.02, mirror_location=1.0, electric_field=0.25 * EV).resolved_for(edl),
+                                                   use_middle_scheme=False), "mixed", 3, dict(mirror=1.0, n_random=4 * 62)
+    yield "bulk_tgnh_middle_double", bulk, P(max_drude_distance=0.02).resolved_for(bulk), "double", 3, {}
     rag = vv.make_ragged(seed=1, n_molecules=24, max_size=20, scattered_molecules=0)
     yield "ragged_mixed", rag, P(max_drude_distance=0.02, mirror_location=1.0, electric_field=1e-22).resolved_for(rag), "mixed", 3, dict(mirror=1.0, n_random=8 * rag.n)
 
 
 def main():
+    only = sys.argv[1:]                 # name prefixes; existing fixtures are left untouched unless named
     for name, spec, params, mode, steps, kw in cases():
+        if only and not any(name.startswith(o) for o in only):
+            continue
         cos = kw.pop("cos", False)
         host = vv.make_state(spec, mode, **kw)
         inv_box_z = 1.0 / host.box[2] if cos else 0.0
