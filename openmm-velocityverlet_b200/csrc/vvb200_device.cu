@@ -153,7 +153,7 @@ struct KParams {
 };
 
 enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
-enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2, VAR_SCALE_DELTA = 3 };
+enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2, VAR_SCALE_DELTA = 3, VAR_FINISH = 4 };
 
 // tileMolInfo word: bits 0-10 first slot in tile, bits 11-21 count, bit 31 = not contiguous
 #define MOLINFO_FIRST(w) ((w) & 0x7FF)
@@ -1714,6 +1714,16 @@ extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, voi
         return VVB200_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t st = (cudaStream_t) stream;
+    if (p->tiled && envInt("VVB200_FUSED_FINISH", 1)) {
+        // integrateMiddlePos3 + applyHardWallConstraints (+ the image mirror) in one streaming launch: pass B's tile
+        // machinery with posDelta / oldDelta staged next to velm / posq
+        KParams k = makeParams(p, b, nullptr);
+        k.posDelta = b->pos_delta;
+        k.oldDelta = d->oldDelta;
+        CUDA_TRY((dispatchB<VAR_FINISH>(p->precision, false, k, d->numSM, st)));
+        p->launches++;
+        return VVB200_OK;
+    }
     const int grid = elementwiseGrid(p, p->N);
     const int nPairs = (int) p->drudePairs.size() / 2;
     const bool hw = p->par.max_drude_distance > 0 && nPairs > 0;

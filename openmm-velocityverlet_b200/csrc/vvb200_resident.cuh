@@ -33,6 +33,7 @@ template <int MODE, int KICK, int VARIANT, bool EXTRA> struct StageR {
     typename Prec<MODE>::real4 corr[CORR ? PADT : 1];
     long long f[3][FORCE ? PADT : 2];
     typename Prec<MODE>::mixed cbar[EXTRA ? MAXMOL + 8 : 2];
+    typename Prec<MODE>::mixed4 pd[1], od[1];      // only the streaming finish variant stages posDelta / oldDelta
 };
 
 template <int MODE, int KICK, int VARIANT, bool EXTRA> constexpr size_t smemBytesR(int tiles) {

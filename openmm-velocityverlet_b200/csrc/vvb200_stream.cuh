@@ -683,6 +683,8 @@ template <int MODE, int VARIANT, bool EXTRA> struct StageB {
     typename Prec<MODE>::real4 corr[CORR ? PADT : 1];
     long long f[3][FORCE ? PADT : 2];
     typename Prec<MODE>::mixed cbar[EXTRA ? MAXMOL + 8 : 2];
+    typename Prec<MODE>::mixed4 pd[VARIANT == VAR_FINISH ? PADT : 1];   // posDelta / oldDelta after OpenMM's constraints
+    typename Prec<MODE>::mixed4 od[VARIANT == VAR_FINISH ? PADT : 1];
 };
 
 template <int MODE, int VARIANT, bool EXTRA> constexpr size_t smemBytesB(int stages) {
@@ -834,7 +836,9 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
         const mixed vq0[3] = {vq[0], vq[1], vq[2]};
         bool writeVel = cx.writeAllVel && ws != 0;
 
-        if (isNH) {
+        if (VARIANT == VAR_FINISH) {
+            // no thermostat here: it ran before OpenMM's position constraints (vvb200_middle_thermostat_delta)
+        } else if (isNH) {
             // removePeriodicVelocityBias (cosineAccelerate.cu:63-71)
             if (cosine) { vs[0] -= Vb * cphs; vq[0] -= Vb * cq; }
             // bias-removed molecular velocity: V' = V - Vb*cbar e_x
@@ -901,7 +905,24 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
         }
 
         bool writePos = false;
-        if (VARIANT == VAR_VV_FIRST) {
+        if constexpr (VARIANT == VAR_FINISH) {
+            // integrateMiddlePos3 (middle.cu:66-100): v += (posDelta - oldDelta) / dt, x += posDelta, for this particle
+            // and (redundantly, for the hard wall) its partner
+            const mixed invDt = 1 / stepSize;
+            if (ws != 0) {
+                const mixed4 d = st.pd[sl], o = st.od[sl];
+                vs[0] += (d.x - o.x) * invDt; vs[1] += (d.y - o.y) * invDt; vs[2] += (d.z - o.z) * invDt;
+                ds[0] = d.x; ds[1] = d.y; ds[2] = d.z;
+#pragma unroll
+                for (int k = 0; k < 3; k++) xs[k] += ds[k];
+                writePos = writeVel = true;
+            }
+            if (role != VVB200_ROLE_NONE && wq != 0) {
+                const mixed4 d = st.pd[psl], o = st.od[psl];
+                vq[0] += (d.x - o.x) * invDt; vq[1] += (d.y - o.y) * invDt; vq[2] += (d.z - o.z) * invDt;
+                dq[0] = d.x; dq[1] = d.y; dq[2] = d.z;
+            }
+        } else if (VARIANT == VAR_VV_FIRST) {
             // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
             // particle and (redundantly) its partner
             for (int who = 0; who < 2; who++) {
@@ -1122,7 +1143,7 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
     gridDepWait();      // PDL: everything above overlapped pass A's last-block reduction and NH chains
 
     const bool cosine = EXTRA && p.cosine;
-    const bool useCOM = p.useCOM;
+    const bool useCOM = p.useCOM && VARIANT != VAR_FINISH;      // the finish variant does not touch the thermostat
 
     if (tid >= CTHREADS_B) {
         // ===== producer warp (all lanes stay: the gather fallback uses them) =====
@@ -1156,6 +1177,7 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
                 if (Stage::POSQ) bytes += cnt * (uint32_t) sizeof(real4);
                 if (Stage::CORR) bytes += cnt * (uint32_t) sizeof(real4);
                 if (Stage::FORCE) bytes += 3u * cnt * 8u;
+                if (VARIANT == VAR_FINISH) bytes += 2u * cnt * (uint32_t) sizeof(mixed4);
                 if (nMol > 0 && !gather) bytes += nMol * (uint32_t) sizeof(mixed4) + cbcnt * (uint32_t) sizeof(mixed);
                 mbarArriveExpectTx(full + s, bytes);
                 bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
@@ -1166,6 +1188,10 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
                     bulkLoad(st.f[0], p.force + a0, cnt * 8u, full + s);
                     bulkLoad(st.f[1], p.force + a0 + p.paddedN, cnt * 8u, full + s);
                     bulkLoad(st.f[2], p.force + a0 + 2 * (size_t) p.paddedN, cnt * 8u, full + s);
+                }
+                if (VARIANT == VAR_FINISH) {
+                    bulkLoad(st.pd, reinterpret_cast<const mixed4 *>(p.posDelta) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
+                    bulkLoad(st.od, reinterpret_cast<const mixed4 *>(p.oldDelta) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
                 }
                 if (nMol > 0 && !gather) {
                     bulkLoad(st.comV, comV + d1.x, nMol * (uint32_t) sizeof(mixed4), full + s);

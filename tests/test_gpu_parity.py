@@ -364,5 +364,5 @@ def test_constrained_flow_matches_fused(vv, vo, cos, step_path):
     torch.cuda.synchronize()
     ha, hb = a.to_host(), b.to_host()
     assert np.array_equal(hb.velm, ha.velm) and np.array_equal(hb.posq, ha.posq) and np.array_equal(hb.corr, ha.corr)
-    # kick, reduce, scale+delta, finish, hard wall; reduce + scale+delta are one launch when the system is resident
-    assert pb.launch_count == 3 * (4 if step_path == "resident" else 5)
+    # kick | reduce + scale+delta (one launch when the system is resident) | finish + hard wall (one launch)
+    assert pb.launch_count == 3 * (3 if step_path == "resident" else 4)
