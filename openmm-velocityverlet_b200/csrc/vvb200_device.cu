@@ -153,7 +153,7 @@ struct KParams {
 };
 
 enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
-enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2, VAR_SCALE_DELTA = 3, VAR_FINISH = 4 };
+enum { VAR_MIDDLE = 0, VAR_VV_FIRST = 1, VAR_SCALE_ONLY = 2, VAR_SCALE_DELTA = 3, VAR_FINISH = 4, VAR_VV_POSITIONS = 5 };
 
 // tileMolInfo word: bits 0-10 first slot in tile, bits 11-21 count, bit 31 = not contiguous
 #define MOLINFO_FIRST(w) ((w) & 0x7FF)
@@ -1789,6 +1789,14 @@ extern "C" int vvb200_vv_positions(vvb200_plan *p, const vvb200_buffers *b, void
     }
     cudaStream_t st = (cudaStream_t) stream;
     vvb200_device_state *d = p->dev;
+    if (p->tiled && envInt("VVB200_FUSED_FINISH", 1)) {
+        // velocityVerletIntegratePositions + applyHardWallConstraints (+ the image mirror) in one streaming launch
+        KParams k = makeParams(p, b, nullptr);
+        k.posDelta = b->pos_delta;
+        CUDA_TRY((dispatchB<VAR_VV_POSITIONS>(p->precision, false, k, d->numSM, st)));
+        p->launches++;
+        return VVB200_OK;
+    }
     const int grid = elementwiseGrid(p, p->N);
     const int nPairs = (int) p->drudePairs.size() / 2;
     const bool hw = p->par.max_drude_distance > 0 && nPairs > 0;

@@ -683,7 +683,8 @@ template <int MODE, int VARIANT, bool EXTRA> struct StageB {
     typename Prec<MODE>::real4 corr[CORR ? PADT : 1];
     long long f[3][FORCE ? PADT : 2];
     typename Prec<MODE>::mixed cbar[EXTRA ? MAXMOL + 8 : 2];
-    typename Prec<MODE>::mixed4 pd[VARIANT == VAR_FINISH ? PADT : 1];   // posDelta / oldDelta after OpenMM's constraints
+    // posDelta (and, middle scheme, oldDelta) after OpenMM's position constraints
+    typename Prec<MODE>::mixed4 pd[VARIANT == VAR_FINISH || VARIANT == VAR_VV_POSITIONS ? PADT : 1];
     typename Prec<MODE>::mixed4 od[VARIANT == VAR_FINISH ? PADT : 1];
 };
 
@@ -836,8 +837,8 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
         const mixed vq0[3] = {vq[0], vq[1], vq[2]};
         bool writeVel = cx.writeAllVel && ws != 0;
 
-        if (VARIANT == VAR_FINISH) {
-            // no thermostat here: it ran before OpenMM's position constraints (vvb200_middle_thermostat_delta)
+        if (VARIANT == VAR_FINISH || VARIANT == VAR_VV_POSITIONS) {
+            // no thermostat here: it ran before OpenMM's position constraints
         } else if (isNH) {
             // removePeriodicVelocityBias (cosineAccelerate.cu:63-71)
             if (cosine) { vs[0] -= Vb * cphs; vq[0] -= Vb * cq; }
@@ -921,6 +922,24 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
                 const mixed4 d = st.pd[psl], o = st.od[psl];
                 vq[0] += (d.x - o.x) * invDt; vq[1] += (d.y - o.y) * invDt; vq[2] += (d.z - o.z) * invDt;
                 dq[0] = d.x; dq[1] = d.y; dq[2] = d.z;
+            }
+        } else if constexpr (VARIANT == VAR_VV_POSITIONS) {
+            // velocityVerletIntegratePositions (velocityVerlet.cu:35-68): x += posDelta, v = posDelta / dt
+            if (ws != 0) {
+                const mixed4 d = st.pd[sl];
+                ds[0] = d.x; ds[1] = d.y; ds[2] = d.z;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    vs[k] = (mixed) (invStepSize * ds[k]);
+                    xs[k] += ds[k];
+                }
+                writePos = writeVel = true;
+            }
+            if (role != VVB200_ROLE_NONE && wq != 0) {
+                const mixed4 d = st.pd[psl];
+                dq[0] = d.x; dq[1] = d.y; dq[2] = d.z;
+#pragma unroll
+                for (int k = 0; k < 3; k++) vq[k] = (mixed) (invStepSize * dq[k]);
             }
         } else if (VARIANT == VAR_VV_FIRST) {
             // half kick with the forces of the current positions (velocityVerlet.cu:14-27), for this
@@ -1143,7 +1162,7 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
     gridDepWait();      // PDL: everything above overlapped pass A's last-block reduction and NH chains
 
     const bool cosine = EXTRA && p.cosine;
-    const bool useCOM = p.useCOM && VARIANT != VAR_FINISH;      // the finish variant does not touch the thermostat
+    const bool useCOM = p.useCOM && VARIANT != VAR_FINISH && VARIANT != VAR_VV_POSITIONS;   // these two do not touch the thermostat
 
     if (tid >= CTHREADS_B) {
         // ===== producer warp (all lanes stay: the gather fallback uses them) =====
@@ -1178,6 +1197,7 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
                 if (Stage::CORR) bytes += cnt * (uint32_t) sizeof(real4);
                 if (Stage::FORCE) bytes += 3u * cnt * 8u;
                 if (VARIANT == VAR_FINISH) bytes += 2u * cnt * (uint32_t) sizeof(mixed4);
+                if (VARIANT == VAR_VV_POSITIONS) bytes += cnt * (uint32_t) sizeof(mixed4);
                 if (nMol > 0 && !gather) bytes += nMol * (uint32_t) sizeof(mixed4) + cbcnt * (uint32_t) sizeof(mixed);
                 mbarArriveExpectTx(full + s, bytes);
                 bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
@@ -1189,6 +1209,8 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
                     bulkLoad(st.f[1], p.force + a0 + p.paddedN, cnt * 8u, full + s);
                     bulkLoad(st.f[2], p.force + a0 + 2 * (size_t) p.paddedN, cnt * 8u, full + s);
                 }
+                if (VARIANT == VAR_VV_POSITIONS)
+                    bulkLoad(st.pd, reinterpret_cast<const mixed4 *>(p.posDelta) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
                 if (VARIANT == VAR_FINISH) {
                     bulkLoad(st.pd, reinterpret_cast<const mixed4 *>(p.posDelta) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
                     bulkLoad(st.od, reinterpret_cast<const mixed4 *>(p.oldDelta) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
