@@ -96,9 +96,9 @@ __device__ __forceinline__ void consumerBarrier() { asm volatile("bar.sync 1, %0
 //   d0 = (t0, t1, m0, nMol)   d1 = (molFirst or -1, 0, 0, 0)
 // molFirst >= 0: the tile's thermostat molecules are the consecutive ids molFirst .. molFirst+nMol-1
 
-template <int MODE, bool EXTRA> struct StageA {
+template <int MODE, bool EXTRA, bool FORCE = true> struct StageA {      // FORCE = false: the reduce-only variant (KICK_NONE)
     typename Prec<MODE>::mixed4 velm[PADT];
-    long long f[3][PADT];
+    long long f[3][FORCE ? PADT : 2];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
     int32_t desc[8];
@@ -124,8 +124,8 @@ template <int MODE, bool EXTRA> struct ScratchA {
 
 __host__ __device__ constexpr size_t roundUp128(size_t x) { return (x + 127) / 128 * 128; }
 
-template <int MODE, bool EXTRA> constexpr size_t smemBytesA(int stages) {
-    return roundUp128(sizeof(StageA<MODE, EXTRA>)) * stages + roundUp128(sizeof(ScratchA<MODE, EXTRA>)) + 16 * stages + 128;
+template <int MODE, bool EXTRA, bool FORCE> constexpr size_t smemBytesA(int stages) {
+    return roundUp128(sizeof(StageA<MODE, EXTRA, FORCE>)) * stages + roundUp128(sizeof(ScratchA<MODE, EXTRA>)) + 16 * stages + 128;
 }
 
 // lanes that cooperate on one molecule's centre of mass
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(cons
     typedef typename P::real4 real4;
     typedef typename P::mixed4 mixed4;
     typedef typename P::real3 real3;
-    typedef StageA<MODE, EXTRA> Stage;
+    typedef StageA<MODE, EXTRA, KICK != KICK_NONE> Stage;
     typedef ScratchA<MODE, EXTRA> Scratch;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     __shared__ NhcDevice nhcS;
