@@ -133,7 +133,15 @@ enum {
     VVB200_ARR_IMAGE_PAIRS,             /* imagePairsVec, :885-887 */
     VVB200_ARR_ELECTROLYTE,             /* particlesElectrolyteVec, :954 */
     VVB200_ARR_TILE_START,              /* new: molecule-aligned tile boundaries of the fused path */
-    VVB200_ARR_SLOT_META                /* new: packed per-slot topology word of the fused path */
+    VVB200_ARR_SLOT_META,               /* new: packed per-slot topology word of the fused path */
+    VVB200_ARR_TILE_MOL_OFFSET,         /* new: [tiles+1] prefix into TILE_MOL_LIST */
+    VVB200_ARR_TILE_MOL_LIST,           /* new: thermostat molecules of each tile, in order of first appearance */
+    VVB200_ARR_TILE_MOL_FRAG,           /* new: per entry of TILE_MOL_LIST: fragment index, or -1 for a whole molecule */
+    VVB200_ARR_SPLIT_MOL_ID,            /* new: thermostat molecules longer than a tile (cut into fragments) */
+    VVB200_ARR_SPLIT_FRAG_OFFSET,       /* new: [cut molecules+1] prefix into SPLIT_FRAG_LIST */
+    VVB200_ARR_SPLIT_FRAG_LIST,         /* new: fragment indices of each cut molecule, in tile order */
+    VVB200_ARR_IMAGE_OF                 /* new: [N] image particle mirrored by each particle's thread or -1; empty when
+                                           the image update is not fused into pass B */
 };
 int vvb200_plan_get_int_array(const vvb200_plan *plan, int which, const int32_t **ptr, int64_t *len);
 

@@ -15,6 +15,8 @@ INT_ARRAYS = {
     "particlesNH": 0, "moleculesNH": 1, "particleMolId": 2, "drudePairs": 3, "sortedByMol": 4,
     "particlesInMolecules": 5, "normalNH": 6, "pairsNH": 7, "normalLD": 8, "pairsLD": 9,
     "imagePairs": 10, "electrolyte": 11, "tileStart": 12, "slotMeta": 13,
+    "tileMolOffset": 14, "tileMolList": 15, "tileMolFrag": 16, "splitMolId": 17, "splitFragOffset": 18,
+    "splitFragList": 19, "imageOf": 20,
 }
 F64_ARRAYS = {"moleculeMasses": 0, "moleculeInvMasses": 1, "dof": 2, "etaMass": 3, "NkbT": 4, "invMassTotal": 5, "dofGlobal": 6}
 

@@ -657,6 +657,13 @@ extern "C" int vvb200_plan_get_int_array(const vvb200_plan *p, int which, const 
     case VVB200_ARR_IMAGE_PAIRS: v = &p->imagePairs; break;
     case VVB200_ARR_ELECTROLYTE: v = &p->particlesElectrolyte; break;
     case VVB200_ARR_TILE_START: v = &p->tileStart; break;
+    case VVB200_ARR_TILE_MOL_OFFSET: v = &p->tileMolOffset; break;
+    case VVB200_ARR_TILE_MOL_LIST: v = &p->tileMolList; break;
+    case VVB200_ARR_TILE_MOL_FRAG: v = &p->tileMolFrag; break;
+    case VVB200_ARR_SPLIT_MOL_ID: v = &p->splitMolId; break;
+    case VVB200_ARR_SPLIT_FRAG_OFFSET: v = &p->splitFragOffset; break;
+    case VVB200_ARR_SPLIT_FRAG_LIST: v = &p->splitFragList; break;
+    case VVB200_ARR_IMAGE_OF: v = &p->imageOf; break;
     case VVB200_ARR_SLOT_META:
         *ptr = reinterpret_cast<const int32_t *>(p->slotMeta.data());
         *len = (int64_t) p->slotMeta.size();

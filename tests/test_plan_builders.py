@@ -147,3 +147,67 @@ def test_large_builder_is_linear_time(vv):
     dt = time.perf_counter() - t0
     assert plan.tiled and dt < 5.0
     assert plan.int_array("particlesNH").size == spec.n
+
+
+@pytest.mark.parametrize("chains,chain_len,solvent", [(1, 330, 6), (3, 700, 40), (7, 1300, 500), (2, 5000, 0)])
+def test_cut_molecules_fragment_tables(vv, chains, chain_len, solvent):
+    """thermostat molecules longer than a tile: cut between Drude pairs only; every (tile, molecule) piece of a cut molecule
+    is one fragment; a molecule's fragments are listed in tile order and together cover exactly its COM members; whole
+    molecules stay inside one tile"""
+    spec = vv.make_polymer(chains, chain_len, solvent, adjacent=True)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    plan = vv.Plan(spec, params)
+    assert plan.tiled
+    ts = plan.int_array("tileStart")
+    n_tiles = len(ts) - 1
+    assert ts[0] == 0 and ts[-1] == spec.n and np.all(np.diff(ts) > 0) and np.all(np.diff(ts) <= 512)
+    tile_of = np.searchsorted(ts, np.arange(spec.n), side="right") - 1
+    assert np.array_equal(tile_of[spec.drude_pairs[:, 0]], tile_of[spec.drude_pairs[:, 1]])       # pairs are never cut
+    off, mols, frag = plan.int_array("tileMolOffset"), plan.int_array("tileMolList"), plan.int_array("tileMolFrag")
+    split, foff, flist = plan.int_array("splitMolId"), plan.int_array("splitFragOffset"), plan.int_array("splitFragList")
+    assert off.size == n_tiles + 1 and off[-1] == mols.size == frag.size and np.all(np.diff(off) <= 128)
+    assert split.size == chains and np.all(np.diff(split) > 0) and foff.size == split.size + 1 and foff[-1] == flist.size
+    n_frag = int((frag >= 0).sum())
+    assert sorted(flist.tolist()) == list(range(n_frag))                     # every fragment belongs to exactly one molecule
+    meta = plan.int_array("slotMeta")
+    local = (meta & 0x7FF).astype(np.int64)
+    tile_of_entry = np.searchsorted(off, np.arange(mols.size), side="right") - 1
+    frag_entry = {int(f): k for k, f in enumerate(frag) if f >= 0}
+    for k, m in enumerate(split):
+        fr = flist[foff[k]:foff[k + 1]]
+        entries = [frag_entry[int(f)] for f in fr]
+        assert all(mols[e] == m for e in entries)
+        tiles = tile_of_entry[entries]
+        assert np.all(np.diff(tiles) > 0) and len(tiles) >= 2                 # tile order, really cut
+        members = np.flatnonzero(spec.mol_id == m)
+        assert set(tile_of[members]) == set(tiles.tolist())                   # one fragment per tile the molecule touches
+        # the slot words of the molecule's particles point at the molecule's entry of their tile
+        for e in entries:
+            t = tile_of_entry[e]
+            inside = members[tile_of[members] == t]
+            assert np.all(local[inside] == e - off[t])
+    # whole (uncut) thermostat molecules: one tile, no fragment
+    whole = np.setdiff1d(np.unique(mols), split)
+    for m in whole[:300]:
+        members = np.flatnonzero(spec.mol_id == m)
+        assert len(set(tile_of[members])) == 1
+    assert np.all(frag[np.isin(mols, whole)] == -1)
+
+
+def test_image_of_table(vv):
+    """fused image update: every parent's thread knows its image; absent when a parent has two images"""
+    spec = vv.make_edl(40, 300, 3)
+    params = vv.Params(mirror_location=1.0).resolved_for(spec)
+    plan = vv.Plan(spec, params)
+    image_of = plan.int_array("imageOf")
+    assert image_of.size == spec.n
+    assert np.array_equal(image_of[spec.image_pairs[:, 1]], spec.image_pairs[:, 0])
+    assert (image_of >= 0).sum() == spec.image_pairs.shape[0]
+    meta = plan.int_array("slotMeta")
+    assert np.array_equal((meta >> 14) & 1, (image_of >= 0).astype(np.uint32))
+    twice = dataclasses.replace(spec, image_pairs=np.concatenate([spec.image_pairs, spec.image_pairs[:1] + np.array([[1, 0]], np.int32)]))
+    try:
+        plan2 = vv.Plan(twice.finalize(mol_id=spec.mol_id) if hasattr(twice, "finalize") else twice, params)
+        assert plan2.int_array("imageOf").size == 0                                            # falls back to the image kernel
+    except vv.VVB200Error:
+        pass    # the builder may refuse the doubled pair for other reasons (image inside a thermostat): also fine
