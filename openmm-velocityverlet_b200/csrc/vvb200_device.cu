@@ -149,6 +149,7 @@ struct KParams {
     // streaming kernels: the tile range of this launch (the whole system unless the host pipeline splits a step) and
     // whether its sums are added to those already in nhc->red
     int tileBegin, tileEnd, accumulateRed;
+    int pdl;     // launch with programmatic stream serialization (host side only)
     unsigned int *gridGen;   // generation word of its grid barrier
 };
 
@@ -709,6 +710,7 @@ struct vvb200_device_state {
     NhcDevice *nhc = nullptr;
     unsigned int *counter = nullptr;   // [0] arrival counter of the last-block reductions, [1] grid-barrier generation
     int64_t residentLaunches = 0;
+    int pdl = 1;                       // VVB200_PDL at upload time
     int residentMode = -1;
     int residentMaxParticles = -1;     // -1: from the environment (VVB200_RESIDENT_MAX_PARTICLES, default 120000)             // -1: from the environment (VVB200_RESIDENT, default on), 0 off, 1 on
     bool extraForcesValid = false;   // VV scheme: forceExtra is zero until the first second half
@@ -793,6 +795,8 @@ static void fillNhcHost(const vvb200_plan *p, NhcDevice &h) {
     h.invMassTotal = 1.0 / p->totalMassGlobal;
 }
 
+static int envInt(const char *name, int dflt);
+
 extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     if (!p) {
         vvb200_set_error("vvb200_plan_upload: null plan");
@@ -805,6 +809,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     CUDA_TRY(cudaGetDevice(&d->device));
     CUDA_TRY(cudaDeviceGetAttribute(&d->numSM, cudaDevAttrMultiProcessorCount, d->device));
     d->numTiles = (int) p->tileStart.size() - 1;
+    d->pdl = envInt("VVB200_PDL", 1) ? 1 : 0;
 
     // per tile-local molecule: first slot, count, contiguity
     std::vector<int32_t> molInfo(p->tileMolList.size(), 0);
@@ -946,6 +951,7 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     memset(&k, 0, sizeof k);
     k.N = p->N; k.paddedN = p->paddedN; k.numTiles = d->numTiles;
     k.tileBegin = 0; k.tileEnd = d->numTiles;
+    k.pdl = d->pdl;
     k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
     k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
@@ -1025,7 +1031,6 @@ static LaunchCfg configure(F kernel, size_t (*smemBytes)(int), const char *stage
 // touching data -- the ~2-3 us of launch latency and prologue per kernel leave the critical path (VVB200_PDL=0: off).
 template <class... Args>
 static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, int blockThreads, size_t smem, cudaStream_t st, const KParams &k) {
-    static const int pdl = envInt("VVB200_PDL", 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(blockThreads);
@@ -1035,7 +1040,7 @@ static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, int blockT
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = k.pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, k);
 }
 

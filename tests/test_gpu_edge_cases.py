@@ -308,3 +308,24 @@ def test_edl_step_is_one_launch(vv, vo, step_path):
     img = spec.image_pairs[:, 0]
     assert np.array_equal(got.posq[img, 3], host.posq[img, 3])            # the images keep their own charges
     assert np.array_equal(got.posq[img, :2], got.posq[spec.image_pairs[:, 1], :2])   # x, y copied bit for bit
+
+
+def test_launch_overlap_changes_nothing(vv, vo, monkeypatch):
+    """programmatic dependent launch (each streaming kernel is scheduled while its predecessor drains and waits at
+    griddepcontrol.wait before touching data): 1,500 steps of a 220k-particle box with it on and off end bitwise
+    identical -- a kernel that started reading early would show up here"""
+    spec = vv.make_bulk_ionic_liquid(6000)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", force_sigma=1.0)
+    monkeypatch.setenv("VVB200_RESIDENT", "0")
+    outs = []
+    for pdl in ("1", "0"):
+        monkeypatch.setenv("VVB200_PDL", pdl)
+        plan = vv.Plan(spec, params, "mixed").upload()
+        bufs = vv.DeviceBuffers(host)
+        plan.step(bufs, steps=1500)
+        assert plan.launch_count == 3000
+        outs.append((bufs.to_host(), plan.thermostat_state()))
+    (a, sa), (b, sb) = outs
+    assert np.array_equal(a.velm, b.velm) and np.array_equal(a.posq, b.posq) and np.array_equal(a.corr, b.corr)
+    assert np.array_equal(sa["eta_dot"], sb["eta_dot"]) and np.isfinite(a.velm).all()
