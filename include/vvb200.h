@@ -179,9 +179,12 @@ int vvb200_plan_upload(vvb200_plan *plan, void *stream);
  *   middle scheme: VVIntegrator::stepMiddle body after calcForcesAndEnergy (VVIntegrator.cpp:237-268):
  *       resetExtraForce, Langevin/field/cosine forces, firstIntegrate, [bias remove], scaleVelocity,
  *       [bias restore], secondIntegrate (incl. hard wall), updateImagePositions.
- *   Fused into: pass A (extra forces + kick + COM / group-KE / bias reduction, NH chains advanced by
- *   the last block on the device) and pass B (thermostat scaling + both half drifts + position
- *   write + hard wall), plus a small image gather kernel when image pairs exist.  No host sync. */
+ *   Fused into: pass A (extra forces incl. the Langevin force + kick + COM / group-KE / bias
+ *   reduction, NH chains advanced by the last block on the device) and pass B (thermostat scaling +
+ *   both half drifts + position write + hard wall + image mirror) -- or, for systems of up to
+ *   ~120k particles, ONE launch that keeps the state in shared memory across a grid barrier
+ *   (vvb200_set_resident_mode).  No host sync.  Thermostat molecules longer than a tile (polymers)
+ *   are cut and their centre of mass finished by the last block of pass A. */
 int vvb200_step_middle(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);
 
 /* Velocity-Verlet scheme (VVIntegrator::stepVV, VVIntegrator.cpp:272-338), split where OpenMM
@@ -226,7 +229,7 @@ int vvb200_thermostat(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200
 int vvb200_middle_thermostat_delta(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);
 /* accumulate == 0: integrateMiddlePos1 (posDelta = oldDelta = dt/2 v, :154-158); != 0: integrateMiddlePos2 (+=, :169-173) */
 int vvb200_middle_delta(vvb200_plan *plan, const vvb200_buffers *buf, int accumulate, void *stream);
-int vvb200_middle_finish(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);                                  /* integrateMiddlePos3 + applyHardWallConstraints, :179-212 */
+int vvb200_middle_finish(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);                                  /* integrateMiddlePos3 + applyHardWallConstraints (+ image mirror), :179-212, one launch */
 /* The same for the velocity-Verlet scheme (CudaIntegrateVVStepKernel::firstIntegrate / secondIntegrate,
  * CudaVVKernels.cpp:296-431): velocityVerletIntegrateVelocities (second_half != 0: this step's Langevin force is
  * computed first, like VVIntegrator.cpp:316-325; update_pos_delta != 0: posDelta = dt v) and
