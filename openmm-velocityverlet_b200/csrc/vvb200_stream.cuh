@@ -129,7 +129,9 @@ template <int MODE, bool EXTRA, bool FORCE> constexpr size_t smemBytesA(int stag
 }
 
 // lanes that cooperate on one molecule's centre of mass
+#ifndef COM_LANES
 #define COM_LANES 8
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // pass A: extra forces + kick + molecular COM + group kinetic energies (+ bias moments) + NH chains

@@ -145,7 +145,7 @@ def test_vv_scheme_edl(vv, vo):
     check_thermostat(plan, oracle, "mixed")
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("precision", ["mixed", "double"])
 def test_ragged_topologies(vv, vo, seed, precision):
     """ragged molecule sizes, non-adjacent Drude partners, massless sites, Langevin molecules with Drude
