@@ -1046,7 +1046,7 @@ static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, int blockT
 
 template <int MODE, int KICK, bool EXTRA>
 static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
-    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA, KICK != KICK_NONE>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", MINBLOCKS_A, BTHREADS, 8);
+    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA, KICK != KICK_NONE>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", passABlocks(KICK), BTHREADS, 8);
     k.stagesA = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
     return launchStreaming(kick_reduce_kernel<MODE, KICK, EXTRA>, grid, BTHREADS, cfg.smem, st, k);

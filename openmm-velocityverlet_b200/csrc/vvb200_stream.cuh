@@ -128,6 +128,14 @@ template <int MODE, bool EXTRA, bool FORCE> constexpr size_t smemBytesA(int stag
     return roundUp128(sizeof(StageA<MODE, EXTRA, FORCE>)) * stages + roundUp128(sizeof(ScratchA<MODE, EXTRA>)) + 16 * stages + 128;
 }
 
+// co-resident blocks per SM pass A is compiled for.  The reduce-only variant (no forces staged, no kick) is bound by
+// instruction latency, not bytes, and would fit a fourth block -- but only at 56 registers per thread, and the spills
+// cost more than the extra warps bring (252 vs 226 us for 16.4M particles), so it stays at three like the others.
+#ifndef MINBLOCKS_A_REDUCE
+#define MINBLOCKS_A_REDUCE MINBLOCKS_A
+#endif
+__host__ __device__ constexpr int passABlocks(int kick) { return kick == KICK_NONE ? MINBLOCKS_A_REDUCE : MINBLOCKS_A; }
+
 // lanes that cooperate on one molecule's centre of mass
 #ifndef COM_LANES
 #define COM_LANES 8
@@ -562,7 +570,7 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
 }
 
 template <int MODE, int KICK, bool EXTRA>
-__global__ void __launch_bounds__(BTHREADS, MINBLOCKS_A) kick_reduce_kernel(const KParams p) {
+__global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kernel(const KParams p) {
     typedef Prec<MODE> P;
     typedef typename P::real real;
     typedef typename P::mixed mixed;
