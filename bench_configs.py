@@ -106,15 +106,19 @@ def main():
         # the flow used when OpenMM constraints sit between the sub-steps (both example scripts use HBonds):
         # kick | thermostat_delta | finish = 440 B/particle (mixed); OpenMM's own solver launches are not included
         split_us = None
-        if params.use_middle_scheme and not plan.random_request:
+        if params.use_middle_scheme:
             pb = vv.Plan(spec, params, mode).upload()
             sb = vv.DeviceBuffers(host, with_pos_delta=True)
 
+            split_ri = [0]
+
             def run_split(k):
                 for _ in range(k):
-                    pb.middle_kick(sb, inv_box_z=inv_box_z)
+                    pb.middle_kick(sb, inv_box_z=inv_box_z, random_index=split_ri[0])
                     pb.middle_thermostat_delta(sb, inv_box_z=inv_box_z)
                     pb.middle_finish(sb)
+                    if pb.random_request:      # wrap inside the injected stream (timing only)
+                        split_ri[0] = (split_ri[0] + pb.random_request) % max(1, host.random.shape[0] - 2 * pb.random_request)
             run_split(5)
             torch.cuda.synchronize()
             e0.record(stream)

@@ -229,7 +229,10 @@ int vvb200_thermostat(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200
 int vvb200_middle_thermostat_delta(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args, void *stream);
 /* accumulate == 0: integrateMiddlePos1 (posDelta = oldDelta = dt/2 v, :154-158); != 0: integrateMiddlePos2 (+=, :169-173) */
 int vvb200_middle_delta(vvb200_plan *plan, const vvb200_buffers *buf, int accumulate, void *stream);
-int vvb200_middle_finish(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);                                  /* integrateMiddlePos3 + applyHardWallConstraints (+ image mirror), :179-212, one launch */
+/* integrateMiddlePos3 + applyHardWallConstraints (CudaVVKernels.cpp:179-212) AND ModifyImageChargeKernel::updateImagePositions
+ * (:904-934): images follow their parents inside this call (one launch on the tiled path), so the glue's
+ * updateImagePositions is a no-op after it.  vvb200_vv_positions below does the same. */
+int vvb200_middle_finish(vvb200_plan *plan, const vvb200_buffers *buf, void *stream);
 /* The same for the velocity-Verlet scheme (CudaIntegrateVVStepKernel::firstIntegrate / secondIntegrate,
  * CudaVVKernels.cpp:296-431): velocityVerletIntegrateVelocities (second_half != 0: this step's Langevin force is
  * computed first, like VVIntegrator.cpp:316-325; update_pos_delta != 0: posDelta = dt v) and

@@ -349,6 +349,34 @@ class Plan:
         b = bufs.c_struct()
         _check(self.lib, self.lib.vvb200_update_image_positions(self.h, C.byref(b), self._stream(stream)))
 
+    def step_constrained(self, bufs, solver, steps=1, random_index=0, inv_box_z=0.0, stream=None):
+        """`steps` steps of the constraint-bearing flow, exactly as the OpenMM glue issues it (csrc/glue/
+        CudaVVKernelsB200.cpp): `solver` plays CudaIntegrationUtilities -- solver.apply_velocity_constraints(bufs) and
+        solver.apply_constraints(bufs) run between the split entry points (CudaVVKernels.cpp:151,176,351,427).
+        bufs needs pos_delta.  Middle scheme: kick | vel. constraints | thermostat + both half drifts into posDelta |
+        pos. constraints | finish (+ hard wall + images).  Velocity-Verlet: thermostat | half kick + posDelta |
+        pos. constraints | positions (+ hard wall + images) | half kick | vel. constraints | thermostat."""
+        req = self.random_request
+        kw = dict(random_index=random_index, inv_box_z=inv_box_z, stream=stream)
+        for _ in range(steps):
+            kw["random_index"] = random_index
+            if self.params.use_middle_scheme:
+                self.middle_kick(bufs, **kw)
+                solver.apply_velocity_constraints(bufs)
+                self.middle_thermostat_delta(bufs, **kw)
+                solver.apply_constraints(bufs)
+                self.middle_finish(bufs, stream=stream)
+            else:
+                self.thermostat(bufs, **kw)
+                self.vv_kick(bufs, False, True, **kw)
+                solver.apply_constraints(bufs)
+                self.vv_positions(bufs, stream=stream)
+                self.vv_kick(bufs, True, False, **kw)
+                solver.apply_velocity_constraints(bufs)
+                self.thermostat(bufs, **kw)
+            random_index += req
+        return random_index
+
     def step(self, bufs, steps=1, random_index=0, inv_box_z=0.0, stream=None):
         """`steps` whole integrator steps with the forces in bufs held fixed; returns the
         random index after the last step (advanced like prepareRandomNumbers)."""

@@ -1434,8 +1434,7 @@ extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffer
         if ((rc = withPosDelta(p, b, &bb, st))) return rc;
         if (hasNH(p) && (rc = generalThermostat(p, &bb, a, false, false, true, st))) return rc;
         if ((rc = vvb200_middle_delta(p, &bb, 1, stream))) return rc;
-        if ((rc = vvb200_middle_finish(p, &bb, stream))) return rc;
-        return vvb200_update_image_positions(p, b, stream);
+        return vvb200_middle_finish(p, &bb, stream);      // position write + hard wall + images
     }
     KParams k = makeParams(p, b, a);
     // the pass-B interval of the split path starts here (the all-reduce and the NHC block are not in it)
@@ -1515,8 +1514,7 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
         if ((rc = vvb200_middle_delta(p, &bb, 0, stream))) return rc;
         if (hasNH(p) && (rc = generalThermostat(p, &bb, a, true, true, true, st))) return rc;
         if ((rc = vvb200_middle_delta(p, &bb, 1, stream))) return rc;
-        if ((rc = vvb200_middle_finish(p, &bb, stream))) return rc;
-        return vvb200_update_image_positions(p, b, stream);
+        return vvb200_middle_finish(p, &bb, stream);      // position write + hard wall + images
     }
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
@@ -1556,8 +1554,7 @@ extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, con
         default: vv_delta_kernel<VVB200_DOUBLE><<<grid, THREADS, 0, st>>>(bb.velm, bb.pos_delta, p->N, p->par.step_size);
         }
         p->launches++;
-        if ((rc = vvb200_vv_positions(p, &bb, stream))) return rc;
-        return vvb200_update_image_positions(p, b, stream);
+        return vvb200_vv_positions(p, &bb, stream);       // position write + hard wall + images
     }
     KParams k = makeParams(p, b, a);
     k.extraForces = p->dev->extraForcesValid ? 1 : 0;
@@ -1727,7 +1724,7 @@ extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, voi
         k.oldDelta = d->oldDelta;
         CUDA_TRY((dispatchB<VAR_FINISH>(p->precision, false, k, d->numSM, st)));
         p->launches++;
-        return VVB200_OK;
+        return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);
     }
     const int grid = elementwiseGrid(p, p->N);
     const int nPairs = (int) p->drudePairs.size() / 2;
@@ -1749,7 +1746,7 @@ extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, voi
     }
     p->launches += hw ? 2 : 1;
     CUDA_TRY(cudaGetLastError());
-    return VVB200_OK;
+    return vvb200_update_image_positions(p, b, stream);      // images follow their parents in every variant of this call
 }
 
 // velocity-Verlet scheme around OpenMM's constraint kernels (CudaVVKernels.cpp:296-431)
@@ -1800,7 +1797,7 @@ extern "C" int vvb200_vv_positions(vvb200_plan *p, const vvb200_buffers *b, void
         k.posDelta = b->pos_delta;
         CUDA_TRY((dispatchB<VAR_VV_POSITIONS>(p->precision, false, k, d->numSM, st)));
         p->launches++;
-        return VVB200_OK;
+        return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);
     }
     const int grid = elementwiseGrid(p, p->N);
     const int nPairs = (int) p->drudePairs.size() / 2;
@@ -1822,7 +1819,7 @@ extern "C" int vvb200_vv_positions(vvb200_plan *p, const vvb200_buffers *b, void
     }
     p->launches += hw ? 2 : 1;
     CUDA_TRY(cudaGetLastError());
-    return VVB200_OK;
+    return vvb200_update_image_positions(p, b, stream);      // images follow their parents in every variant of this call
 }
 
 // ---- state ------------------------------------------------------------------------------------

@@ -234,11 +234,11 @@ def make_polymer(n_chains=3, chain_len=700, n_solvent=40, has_cmm=False, adjacen
     return spec.finalize()
 
 
-def make_edl(n_ion_pairs=511, n_electrode=2496, electrode_molecules=4, name=None):
+def make_edl(n_ion_pairs=511, n_electrode=2496, electrode_molecules=4, name=None, hbond_constraints=False):
     """BASELINE config 3 (examples/run-edl.py): Langevin electrode atoms, NH + external field on the
     electrolyte, one massless image particle per electrolyte particle bonded into its parent's
     molecule (run-edl.py:92-95) -- so electrolyte molecules are NOT contiguous in particle order."""
-    tm, tb, tp, _ = _ion_pair_template(False)
+    tm, tb, tp, tc = _ion_pair_template(hbond_constraints)      # run-edl.py:30 constrains the H bonds of the ions
     n_el = n_ion_pairs * _ION_PAIR_SITES
     n = n_electrode + 2 * n_el
     per = n_electrode // electrode_molecules
@@ -253,6 +253,7 @@ def make_edl(n_ion_pairs=511, n_electrode=2496, electrode_molecules=4, name=None
     masses = np.concatenate([e_masses, np.tile(tm, n_ion_pairs), np.zeros(n_el)])
     spec = SystemSpec(n=n, masses=masses, bonds=bonds,
                       drude_pairs=_tile_template(n_ion_pairs, _ION_PAIR_SITES, tp, n_electrode),
+                      constraints=_tile_template(n_ion_pairs, _ION_PAIR_SITES, tc, n_electrode) if tc.size else np.zeros((0, 2), np.int32),
                       langevin=e_idx, image_pairs=np.stack([images, ions], axis=1), electrolyte=ions,
                       name=name or f"edl_{n_ion_pairs}ip")
     return spec.finalize()

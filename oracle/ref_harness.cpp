@@ -188,6 +188,29 @@ mixed temp[16];
 #undef sumNormalizedKineticEnergies
 #undef scaleVelocity
 
+/* ---- stand-in for OpenMM's constraint solvers between the sub-steps (oracle/constraint_standin.h;
+ *      NOT reference code): applied where the reference calls integration.applyConstraints /
+ *      applyVelocityConstraints (CudaVVKernels.cpp:151,176,351,427) -------------------------------- */
+#define VVC_REAL4 real4
+#define VVC_MIXED4 mixed4
+#define VVC_MIXED mixed
+#if VVREF_GPU
+#define VVC_FN __host__ __device__ inline
+#else
+#define VVC_FN static inline
+#endif
+#include "constraint_standin.h"
+#if VVREF_GPU
+__global__ void standinPositionsKernel(vvc_constraints cs, const real4 *posq, const real4 *corr, const mixed4 *velm, mixed4 *posDelta) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cs.numClusters; c += blockDim.x * gridDim.x)
+        vvc_cluster_positions(cs, c, posq, corr, velm, posDelta);
+}
+__global__ void standinVelocitiesKernel(vvc_constraints cs, const real4 *posq, const real4 *corr, mixed4 *velm) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cs.numClusters; c += blockDim.x * gridDim.x)
+        vvc_cluster_velocities(cs, c, posq, corr, velm);
+}
+#endif
+
 /* ---------------------------------------------------------------------------------------- */
 static const double VVREF_BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0;
 static const double VVREF_AVOGADRO = 6.02214076e23;
@@ -280,6 +303,10 @@ struct vvref_ctx {
         etaDotDot[3][VVREF_MAX_CHAINS], NkbT[3];
     double ke2[3], vscale[3];
     long launches;
+    /* constraint stand-in tables (device memory on the GPU flavour) */
+    vvc_constraints cons;
+    Arr<int> consOffset, consAtoms;
+    Arr<double> consDistance;
 #if VVREF_GPU
     cudaStream_t stream;
 #endif
@@ -499,6 +526,28 @@ static void hardWall(vvref_ctx *c, const vvref_buffers *b, bool middle) {
     }
 }
 
+/* integration.applyConstraints(tol) / applyVelocityConstraints(tol): the stand-in, see above */
+static void applyConstraintsStandin(vvref_ctx *c, const vvref_buffers *b) {
+    if (c->cons.numClusters <= 0) return;
+#if VVREF_GPU
+    standinPositionsKernel<<<(c->cons.numClusters + 127) / 128, 128, 0, c->stream>>>(c->cons, POSQ(b), CORR(b), VELM(b), PDELTA(b));
+#else
+    _Pragma("omp parallel for schedule(static)")
+    for (int k = 0; k < c->cons.numClusters; k++)
+        vvc_cluster_positions(c->cons, k, POSQ(b), CORR(b), VELM(b), PDELTA(b));
+#endif
+}
+static void applyVelocityConstraintsStandin(vvref_ctx *c, const vvref_buffers *b) {
+    if (c->cons.numClusters <= 0) return;
+#if VVREF_GPU
+    standinVelocitiesKernel<<<(c->cons.numClusters + 127) / 128, 128, 0, c->stream>>>(c->cons, POSQ(b), CORR(b), VELM(b));
+#else
+    _Pragma("omp parallel for schedule(static)")
+    for (int k = 0; k < c->cons.numClusters; k++)
+        vvc_cluster_velocities(c->cons, k, POSQ(b), CORR(b), VELM(b));
+#endif
+}
+
 static void nhHalf(vvref_ctx *c, const vvref_buffers *b, double invBoxZ) {
     if (c->nNH > 0) {
         if (c->par.cosAcceleration != 0) {
@@ -591,7 +640,25 @@ vvref_ctx *vvref_create(const vvref_indices *ix, const vvref_params *par, int nu
             c->etaMass[g][k] = ix->etaMass[g * par->numNHChains + k];
     }
     for (int g = 0; g < 3; g++) { c->ke2[g] = 0; c->vscale[g] = 1; }
+    memset(&c->cons, 0, sizeof c->cons);
     return c;
+}
+
+/* cluster tables of the constraint stand-in (host pointers; copied).  numClusters == 0: off. */
+void vvref_set_constraint_standin(vvref_ctx *c, int numClusters, const int32_t *clusterOffset, const int32_t *atoms,
+                                  const double *distance, int iterations) {
+    c->consOffset.release(); c->consAtoms.release(); c->consDistance.release();
+    memset(&c->cons, 0, sizeof c->cons);
+    if (numClusters <= 0) return;
+    const int nCons = clusterOffset[numClusters];
+    c->consOffset.alloc(numClusters + 1); c->consOffset.upload(clusterOffset, numClusters + 1);
+    c->consAtoms.alloc(2 * (size_t) nCons); c->consAtoms.upload(atoms, 2 * (size_t) nCons);
+    c->consDistance.alloc(nCons); c->consDistance.upload(distance, nCons);
+    c->cons.numClusters = numClusters;
+    c->cons.iterations = iterations;
+    c->cons.clusterOffset = c->consOffset.p;
+    c->cons.atoms = c->consAtoms.p;
+    c->cons.distance = c->consDistance.p;
 }
 
 void vvref_destroy(vvref_ctx *c) {
@@ -602,6 +669,7 @@ void vvref_destroy(vvref_ctx *c) {
     c->normalParticlesLD.release(); c->particlesElectrolyte.release(); c->forceExtra.release();
     c->oldDelta.release(); c->comVelm.release(); c->kineticEnergyBufferNH.release();
     c->kineticEnergiesNH.release(); c->vscaleFactorsNH.release(); c->vMaxBuffer.release(); c->stepSize.release();
+    c->consOffset.release(); c->consAtoms.release(); c->consDistance.release();
     delete c;
 }
 
@@ -615,10 +683,12 @@ long vvref_step(vvref_ctx *c, const vvref_buffers *b, int steps, double invBoxZ,
             extraForces(c, b, invBoxZ, randomPos);
             /* firstIntegrate -- CudaVVKernels.cpp:129-159 */
             VVREF_LAUNCH(c, integrateMiddleVel, c->numAtoms, 64, 0, VELM(b), b->force, c->forceExtra.p, c->stepSize.p);
+            applyVelocityConstraintsStandin(c, b);      /* integration.applyVelocityConstraints, :151 */
             VVREF_LAUNCH(c, integrateMiddlePos1, c->numAtoms, 64, 0, VELM(b), PDELTA(b), c->oldDelta.p, c->stepSize.p);
             nhHalf(c, b, invBoxZ);
             /* secondIntegrate -- :161-220 */
             VVREF_LAUNCH(c, integrateMiddlePos2, c->numAtoms, 64, 0, VELM(b), PDELTA(b), c->oldDelta.p, c->stepSize.p);
+            applyConstraintsStandin(c, b);              /* integration.applyConstraints, :176 */
             VVREF_LAUNCH(c, integrateMiddlePos3, c->numAtoms, 64, 0, POSQ(b), CORR(b), PDELTA(b), c->oldDelta.p,
                          VELM(b), c->stepSize.p);
             hardWall(c, b, true);
@@ -630,6 +700,7 @@ long vvref_step(vvref_ctx *c, const vvref_buffers *b, int steps, double invBoxZ,
             double fscale = 0.5 * c->par.stepSize / (double) 0x100000000;
             VVREF_LAUNCH(c, velocityVerletIntegrateVelocities, c->numAtoms, 64, 0, VELM(b), b->force, c->forceExtra.p,
                          PDELTA(b), c->stepSize.p, (mixed) fscale, true);
+            applyConstraintsStandin(c, b);              /* integration.applyConstraints, :351 */
             VVREF_LAUNCH(c, velocityVerletIntegratePositions, c->numAtoms, 64, 0, POSQ(b), CORR(b), PDELTA(b), VELM(b),
                          c->stepSize.p);
             hardWall(c, b, false);
@@ -639,6 +710,7 @@ long vvref_step(vvref_ctx *c, const vvref_buffers *b, int steps, double invBoxZ,
             /* secondIntegrate -- :395-431 */
             VVREF_LAUNCH(c, velocityVerletIntegrateVelocities, c->numAtoms, 64, 0, VELM(b), b->force, c->forceExtra.p,
                          PDELTA(b), c->stepSize.p, (mixed) fscale, false);
+            applyVelocityConstraintsStandin(c, b);      /* integration.applyVelocityConstraints, :427 */
             nhHalf(c, b, invBoxZ);
         }
     }

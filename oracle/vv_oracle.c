@@ -37,6 +37,13 @@ typedef vvo_mixed4 mixed4;
 #define RECIP(x) (1.0f / (x))
 #endif
 
+/* the constraint stand-in (oracle/constraint_standin.h) in this build's types */
+#define VVC_REAL4 vvo_real4
+#define VVC_MIXED4 vvo_mixed4
+#define VVC_MIXED vvo_mixed
+#define VVC_FN static inline
+#include "constraint_standin.h"
+
 static char g_err[512];
 const char *vvo_last_error(void) { return g_err; }
 
@@ -110,6 +117,10 @@ struct vvo_ctx {
     double flatEta[VVO_NUM_TG_MAX * VVO_MAX_CHAINS];
     double flatEtaDot[VVO_NUM_TG_MAX * (VVO_MAX_CHAINS + 1)];
     double flatEtaDotDot[VVO_NUM_TG_MAX * VVO_MAX_CHAINS];
+    /* stand-in for OpenMM's constraint solvers (owning copies of the cluster tables) */
+    vvc_constraints cons;
+    int32_t *consOffset, *consAtoms;
+    double *consDistance;
 };
 
 /* ------------------------------------------------------------------------------------ */
@@ -198,6 +209,7 @@ void vvo_destroy(vvo_ctx *c) {
     free(c->markImage); free(c->drudePairs); free(c->forceExtra); free(c->oldDelta);
     free(c->particlesSortedByMolId); free(c->particlesInMolecules); free(c->normalParticlesNH);
     free(c->pairParticlesNH); free(c->comVelm); free(c->normalParticlesLD); free(c->pairParticlesLD);
+    free(c->consOffset); free(c->consAtoms); free(c->consDistance);
     free(c);
 }
 
@@ -1197,17 +1209,58 @@ static void extraForces(vvo_ctx *c, const vvo_buffers *b, double invBoxZ, unsign
         vvo_cosine_force(c, b, invBoxZ);
 }
 
+/* Stand-in for OpenMM's constraint solvers between the sub-steps (oracle/constraint_standin.h): cluster tables built
+ * by the caller.  numClusters == 0 switches it off (then the calls below are no-ops, like OpenMM's for a System
+ * without constraints). */
+void vvo_set_constraint_standin(vvo_ctx *c, int numClusters, const int32_t *clusterOffset, const int32_t *atoms,
+                                const double *distance, int iterations) {
+    free(c->consOffset); free(c->consAtoms); free(c->consDistance);
+    c->consOffset = c->consAtoms = NULL;
+    c->consDistance = NULL;
+    memset(&c->cons, 0, sizeof c->cons);
+    if (numClusters <= 0)
+        return;
+    const int nCons = clusterOffset[numClusters];
+    c->consOffset = (int32_t *) xcalloc((size_t) numClusters + 1, sizeof(int32_t));
+    c->consAtoms = (int32_t *) xcalloc((size_t) 2 * nCons + 1, sizeof(int32_t));
+    c->consDistance = (double *) xcalloc((size_t) nCons + 1, sizeof(double));
+    memcpy(c->consOffset, clusterOffset, ((size_t) numClusters + 1) * sizeof(int32_t));
+    memcpy(c->consAtoms, atoms, (size_t) 2 * nCons * sizeof(int32_t));
+    memcpy(c->consDistance, distance, (size_t) nCons * sizeof(double));
+    c->cons.numClusters = numClusters;
+    c->cons.iterations = iterations;
+    c->cons.clusterOffset = c->consOffset;
+    c->cons.atoms = c->consAtoms;
+    c->cons.distance = c->consDistance;
+}
+
+/* integration.applyConstraints(tol), CudaVVKernels.cpp:176, 351 */
+void vvo_apply_constraints(vvo_ctx *c, const vvo_buffers *b) {
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < c->cons.numClusters; k++)
+        vvc_cluster_positions(c->cons, k, b->posq, b->posqCorrection, b->velm, b->posDelta);
+}
+
+/* integration.applyVelocityConstraints(tol), CudaVVKernels.cpp:151, 427 */
+void vvo_apply_velocity_constraints(vvo_ctx *c, const vvo_buffers *b) {
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < c->cons.numClusters; k++)
+        vvc_cluster_velocities(c->cons, k, b->posq, b->posqCorrection, b->velm);
+}
+
 void vvo_step(vvo_ctx *c, const vvo_buffers *b, int steps, double invBoxZ, unsigned *randomIndex) {
     for (int s = 0; s < steps; s++) {
         if (c->par.useMiddleScheme) {
             /* VVIntegrator::stepMiddle, VVIntegrator.cpp:232-270; forces are frozen (b->force) */
             extraForces(c, b, invBoxZ, randomIndex);
-            /* firstIntegrate, CudaVVKernels.cpp:129-159 (no constraints in the harness) */
+            /* firstIntegrate, CudaVVKernels.cpp:129-159 */
             vvo_middle_vel(c, b);
+            vvo_apply_velocity_constraints(c, b);
             vvo_middle_pos1(c, b);
             nhHalf(c, b, invBoxZ);
             /* secondIntegrate, CudaVVKernels.cpp:161-220 */
             vvo_middle_pos2(c, b);
+            vvo_apply_constraints(c, b);
             vvo_middle_pos3(c, b);
             vvo_hard_wall(c, b);
             if (c->nImg > 0)
@@ -1217,6 +1270,7 @@ void vvo_step(vvo_ctx *c, const vvo_buffers *b, int steps, double invBoxZ, unsig
             nhHalf(c, b, invBoxZ);
             /* firstIntegrate, CudaVVKernels.cpp:296-382 */
             vvo_vv_velocities(c, b, 1);
+            vvo_apply_constraints(c, b);
             vvo_vv_positions(c, b);
             vvo_hard_wall(c, b);
             if (c->nImg > 0)
@@ -1225,6 +1279,7 @@ void vvo_step(vvo_ctx *c, const vvo_buffers *b, int steps, double invBoxZ, unsig
             extraForces(c, b, invBoxZ, randomIndex);
             /* secondIntegrate, CudaVVKernels.cpp:395-431 */
             vvo_vv_velocities(c, b, 0);
+            vvo_apply_velocity_constraints(c, b);
             nhHalf(c, b, invBoxZ);
         }
     }

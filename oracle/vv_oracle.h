@@ -153,6 +153,15 @@ void vvo_calc_viscosity(vvo_ctx *c, double boxX, double boxY, double boxZ, doubl
  * For stepVV, forcesValid follows VVIntegrator's forcesAreValid flag (frozen forces: no-op). */
 void vvo_step(vvo_ctx *c, const vvo_buffers *b, int steps, double invBoxZ, unsigned *randomIndex);
 
+/* Stand-in for OpenMM's constraint solvers between the sub-steps (oracle/constraint_standin.h): NOT from the
+ * reference and NOT OpenMM's algorithm -- a deterministic operator with the same contract (applyConstraints rewrites
+ * posDelta, applyVelocityConstraints rewrites velm; CudaVVKernels.cpp:151,176,351,427) so that the constraint-bearing
+ * flow is exercised with posDelta != oldDelta.  vvo_step applies it where the reference calls OpenMM. */
+void vvo_set_constraint_standin(vvo_ctx *c, int numClusters, const int32_t *clusterOffset, const int32_t *atoms,
+                                const double *distance, int iterations);
+void vvo_apply_constraints(vvo_ctx *c, const vvo_buffers *b);
+void vvo_apply_velocity_constraints(vvo_ctx *c, const vvo_buffers *b);
+
 /* Toy force field for the 10^4-step statistical tests (NOT from the reference; shared
  * definition with tests/toyforce): F_i = -k_t (x_i - x0_i) for massive non-Drude particles,
  * plus a Drude spring -k_d (x_drude - x_parent) on each pair. Writes fixed-point forces. */

@@ -95,6 +95,9 @@ def oracle_lib(mode):
         lib.vvo_calc_viscosity.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.vvo_toy_forces.argtypes = [C.c_void_p, C.POINTER(_Buffers), C.c_void_p, C.c_double, C.c_double]
         lib.vvo_set_num_threads.argtypes = [C.c_int]
+        lib.vvo_set_constraint_standin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        for name in ("vvo_apply_constraints", "vvo_apply_velocity_constraints"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(_Buffers)]
         _oracle_libs[mode] = lib
     return _oracle_libs[mode]
 
@@ -117,6 +120,100 @@ def propagate_nh_chain(step_size, loops, eta, eta_dot, eta_dotdot, eta_mass, ke2
 
 class OracleError(RuntimeError):
     pass
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-in for OpenMM's constraint solvers (oracle/constraint_standin.h)
+# ---------------------------------------------------------------------------------------------
+class ConstraintStandin:
+    """Cluster tables for the constraint stand-in: connected components of the System's constraint graph (one thread
+    each, like OpenMM's SHAKE clusters), constraints inside a cluster in System order, target distances = the
+    separations in `state` (the geometry the run starts from), `iterations` sweeps.  The same tables go to the C
+    oracle, the reference-kernel harness, the mini-OpenMM and the device helper, so all of them apply one operator."""
+
+    def __init__(self, spec, state, iterations=3):
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+        cons = np.ascontiguousarray(spec.constraints, dtype=np.int32).reshape(-1, 2)
+        self.iterations = int(iterations)
+        if cons.shape[0] == 0:
+            self.n_clusters = 0
+            self.offset = np.zeros(1, np.int32)
+            self.atoms = np.zeros((0, 2), np.int32)
+            self.distance = np.zeros(0, np.float64)
+            return
+        n = spec.n
+        g = coo_matrix((np.ones(len(cons), np.int8), (cons[:, 0], cons[:, 1])), shape=(n, n))
+        _, lab = connected_components(g, directed=False)
+        cl = lab[cons[:, 0]]
+        # clusters numbered by their first constraint; constraints keep System order inside a cluster
+        _, first = np.unique(cl, return_index=True)
+        rank = np.empty(lab.max() + 1, dtype=np.int64)
+        rank[cl[np.sort(first)]] = np.arange(len(first))
+        order = np.argsort(rank[cl], kind="stable")
+        self.atoms = np.ascontiguousarray(cons[order])
+        counts = np.bincount(rank[cl], minlength=len(first))
+        self.offset = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.n_clusters = int(len(first))
+        x = state.positions()
+        self.distance = np.ascontiguousarray(np.linalg.norm(x[self.atoms[:, 0]] - x[self.atoms[:, 1]], axis=1), dtype=np.float64)
+
+    def c_args(self):
+        return (self.n_clusters, _ptr(self.offset), _ptr(self.atoms), _ptr(self.distance), self.iterations)
+
+
+_standin_lib = None
+
+
+def standin_lib():
+    global _standin_lib
+    if _standin_lib is None:
+        path = os.path.join(HERE, "build", "libvvstandin_cuda.so")
+        if not os.path.exists(path):
+            build("oracle")
+        lib = C.CDLL(path)
+        lib.vvstandin_create.restype = C.c_void_p
+        lib.vvstandin_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.vvstandin_destroy.argtypes = [C.c_void_p]
+        lib.vvstandin_apply_constraints.argtypes = [C.c_void_p] * 6
+        lib.vvstandin_apply_velocity_constraints.argtypes = [C.c_void_p] * 5
+        _standin_lib = lib
+    return _standin_lib
+
+
+class DeviceStandin:
+    """The stand-in on device buffers (oracle/standin_cuda.cu): what a GPU test calls between the product's split entry
+    points, where the OpenMM glue calls integration.applyVelocityConstraints / applyConstraints."""
+
+    def __init__(self, standin, precision):
+        self.lib = standin_lib()
+        self._keep = standin
+        self.h = self.lib.vvstandin_create(MODES.index(precision), *standin.c_args())
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.vvstandin_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def apply_constraints(self, bufs, stream=None):
+        import torch
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        rc = self.lib.vvstandin_apply_constraints(self.h, self._p(bufs.posq), self._p(bufs.corr), self._p(bufs.velm),
+                                                  self._p(bufs.pos_delta), st)
+        assert rc == 0, f"stand-in launch failed: cuda error {rc}"
+
+    def apply_velocity_constraints(self, bufs, stream=None):
+        import torch
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+        rc = self.lib.vvstandin_apply_velocity_constraints(self.h, self._p(bufs.posq), self._p(bufs.corr), self._p(bufs.velm), st)
+        assert rc == 0, f"stand-in launch failed: cuda error {rc}"
 
 
 def _bufs(state, pos_delta=None):
@@ -179,6 +276,14 @@ class Oracle:
     def scale_velocity(self, state):
         b = self._b(state)
         self.lib.vvo_scale_velocity(self.h, C.byref(b))
+
+    def set_constraints(self, standin):
+        """switch the constraint stand-in on (ConstraintStandin) or off (None) for vvo_step"""
+        if standin is None:
+            self.lib.vvo_set_constraint_standin(self.h, 0, None, None, None, 0)
+        else:
+            self.lib.vvo_set_constraint_standin(self.h, *standin.c_args())
+        return self
 
     def call(self, kernel, state, *extra):
         b = self._b(state)
@@ -247,6 +352,7 @@ def ref_lib(mode, gpu=False):
         lib.vvref_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(C.c_double)]
         lib.vvref_get_com_velm.argtypes = [C.c_void_p, C.c_void_p]
         lib.vvref_set_num_threads.argtypes = [C.c_int]
+        lib.vvref_set_constraint_standin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _ref_libs[key] = lib
     return _ref_libs[key]
 
@@ -314,6 +420,13 @@ class Reference:
     def scale_velocity(self, state_or_bufs):
         b = self._b_dev(state_or_bufs) if self.gpu else self._b_host(state_or_bufs)
         self.lib.vvref_scale_velocity(self.h, C.byref(b))
+
+    def set_constraints(self, standin):
+        if standin is None:
+            self.lib.vvref_set_constraint_standin(self.h, 0, None, None, None, 0)
+        else:
+            self.lib.vvref_set_constraint_standin(self.h, *standin.c_args())
+        return self
 
     def thermostat_state(self):
         ng, nc = self.num_temp_groups, self.params.num_nh_chains

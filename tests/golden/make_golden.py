@@ -47,6 +47,19 @@ def cases():
     yield "bulk_tgnh_middle_double", bulk, P(max_drude_distance=0.02).resolved_for(bulk), "double", 3, {}
     rag = vv.make_ragged(seed=1, n_molecules=24, max_size=20, scattered_molecules=0)
     yield "ragged_mixed", rag, P(max_drude_distance=0.02, mirror_location=1.0, electric_field=1e-22).resolved_for(rag), "mixed", 3, dict(mirror=1.0, n_random=8 * rag.n)
+    # round 2 (python tests/golden/make_golden.py constrained): the constraint-bearing flow.  OpenMM's solvers between the
+    # sub-steps are the stand-in of oracle/constraint_standin.h (cluster tables stored in the fixture), applied by the
+    # harness where the reference calls integration.applyVelocityConstraints / applyConstraints.
+    cbulk = vv.make_bulk_ionic_liquid(10, hbond_constraints=True)
+    yield "constrained_bulk_middle_mixed", cbulk, P(max_drude_distance=0.02).resolved_for(cbulk), "mixed", 3, dict(constrained=True)
+    yield "constrained_bulk_vv_mixed", cbulk, dataclasses.replace(P(max_drude_distance=0.02).resolved_for(cbulk), use_middle_scheme=False), "mixed", 3, dict(constrained=True)
+    yield "constrained_bulk_hardwall_fires_mixed", cbulk, P(max_drude_distance=0.02).resolved_for(cbulk), "mixed", 2, dict(constrained=True, drude_spread=0.015)
+    yield "constrained_bulk_cosine_middle_mixed", cbulk, P(max_drude_distance=0.02, cos_acceleration=0.02).resolved_for(cbulk), "mixed", 3, dict(constrained=True, cos=True)
+    yield "constrained_bulk_middle_double", cbulk, P(max_drude_distance=0.02).resolved_for(cbulk), "double", 3, dict(constrained=True)
+    cedl = vv.make_edl(n_ion_pairs=6, n_electrode=60, electrode_molecules=3, hbond_constraints=True)
+    yield "constrained_edl_middle_mixed", cedl, P(max_drude_distance=0.02, mirror_location=1.0, electric_field=0.25 * EV).resolved_for(cedl), "mixed", 3, dict(constrained=True, mirror=1.0, n_random=4 * 62)
+    yield "constrained_edl_vv_mixed", cedl, dataclasses.replace(P(max_drude_distance=0.02, mirror_location=1.0, electric_field=0.25 * EV).resolved_for(cedl),
+                                                                use_middle_scheme=False), "mixed", 3, dict(constrained=True, mirror=1.0, n_random=4 * 62)
 
 
 def main():
@@ -54,11 +67,16 @@ def main():
     for name, spec, params, mode, steps, kw in cases():
         if only and not any(name.startswith(o) for o in only):
             continue
+        kw = dict(kw)
         cos = kw.pop("cos", False)
+        constrained = kw.pop("constrained", False)
         host = vv.make_state(spec, mode, **kw)
         inv_box_z = 1.0 / host.box[2] if cos else 0.0
         oracle = vo.Oracle(spec, params, mode, literal=True)          # only supplies the index arrays
         ref = vo.Reference(oracle, gpu=False)
+        cons = vo.ConstraintStandin(spec, host) if constrained else None
+        if cons is not None:
+            ref.set_constraints(cons)
         after = host.copy()
         ref.step(after, steps=steps, inv_box_z=inv_box_z)
         st = ref.thermostat_state()
@@ -73,6 +91,9 @@ def main():
             ke2=st["ke2"], vscale=st["vscale"], velocity_bias=st["velocity_bias"], eta_dot=st["eta_dot"], eta=st["eta"])
         if host.corr is not None:
             out["corr0"], out["corr1"] = host.corr, after.corr
+        if cons is not None:
+            out.update(cons_offset=cons.offset, cons_atoms=cons.atoms, cons_distance=cons.distance,
+                       cons_iterations=cons.iterations)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: N={spec.n} {mode} {steps} steps -> {os.path.getsize(path)} bytes")

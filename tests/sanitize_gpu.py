@@ -10,12 +10,13 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 vv = entry.load_package()
+vo = entry.load_oracle()        # the constraint stand-in (test infrastructure) between the split entry points
 EV = 1.60217662e-22
 import torch  # noqa: E402
 
 P = vv.Params
-bulk = vv.make_bulk_ionic_liquid(40)
-edl = vv.make_edl(n_ion_pairs=12, n_electrode=120, electrode_molecules=3)
+bulk = vv.make_bulk_ionic_liquid(40, hbond_constraints=True)
+edl = vv.make_edl(n_ion_pairs=12, n_electrode=120, electrode_molecules=3, hbond_constraints=True)
 poly = vv.make_polymer(1, 600, 10)
 poly_adj = vv.make_polymer(2, 500, 10, adjacent=True)       # molecules cut across tiles on the fused path
 cases = [(bulk, P(max_drude_distance=0.02), {}), (bulk, P(max_drude_distance=0.02, cos_acceleration=0.02), dict(cos=True)),
@@ -36,9 +37,14 @@ for spec, params, kw in cases:
                 plan.set_resident_mode(resident)
                 bufs = vv.DeviceBuffers(host, with_pos_delta=True)
                 plan.step(bufs, steps=2, inv_box_z=1.0 / host.box[2] if cos else 0.0)
-                if middle and not spec.langevin.size:
-                    plan.middle_kick(bufs); plan.middle_delta(bufs, 0); plan.thermostat(bufs); plan.middle_delta(bufs, 1); plan.middle_finish(bufs)
-                    plan.middle_kick(bufs); plan.middle_thermostat_delta(bufs); plan.middle_finish(bufs)
+                # the constraint-bearing flow (both schemes, Langevin / image systems included) with a live stand-in
+                ibz = 1.0 / host.box[2] if cos else 0.0
+                solver = vo.DeviceStandin(vo.ConstraintStandin(spec, host), mode)
+                ri = plan.step_constrained(bufs, solver, steps=2, random_index=2 * plan.random_request, inv_box_z=ibz)
+                if middle:
+                    plan.middle_kick(bufs, random_index=ri, inv_box_z=ibz); solver.apply_velocity_constraints(bufs)
+                    plan.middle_delta(bufs, 0); plan.thermostat(bufs, inv_box_z=ibz); plan.middle_delta(bufs, 1)
+                    solver.apply_constraints(bufs); plan.middle_finish(bufs)
                 torch.cuda.synchronize()
                 assert bool(torch.isfinite(bufs.velm).all()), "non-finite velocities"
                 print("ok", spec.name, mode, "middle" if middle else "vv", "tiled" if plan.tiled else "general",
