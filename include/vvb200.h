@@ -275,8 +275,10 @@ int vvb200_checkpoint_load(vvb200_plan *plan, const void *host_in, int64_t bytes
 
 /* ---- group temperatures on demand ------------------------------------------------
  * Temperatures of the atom / molecular-COM / Drude groups of the CURRENT velocities, without
- * stepping and without touching the thermostat state: one reduction launch and an 80-byte read
- * back.  Replaces the host path of examples/ommhelper/reporter/drudetemperaturereporter.py:98-129
+ * stepping and without advancing the Nose-Hoover chains or changing the scale factors (the scratch
+ * the thermostat recomputes every step -- reduction vector, comVelm -- is overwritten): one
+ * reduction launch and an 80-byte read back.  A plan that holds one rank's partition reports that
+ * partition (its own DOFs and mass); all-reduce ke2 and dof for the whole box.  Replaces the host path of examples/ommhelper/reporter/drudetemperaturereporter.py:98-129
  * (download of N velocities + numpy) with the thermostat's own definitions
  * (drudeNoseHoover.cu:55-114, DOFs of CudaVVKernels.cpp:516-573).  ke2 = sum m v^2 per group
  * (kJ/mol), temperature = ke2 / (dof kB).  Must not be called between vvb200_middle_kick_reduce
@@ -289,7 +291,8 @@ typedef struct {
 int vvb200_measure_temperatures(vvb200_plan *plan, const vvb200_buffers *buf, const vvb200_step_args *args,
                                 vvb200_temperatures *out, void *stream);
 
-/* Small systems (all tiles co-resident in shared memory, up to ~227k particles in mixed mode) run
+/* Small systems (all tiles co-resident in shared memory; used up to VVB200_RESIDENT_MAX_PARTICLES =
+ * 120,000 particles by default, beyond which the streaming kernels are faster) run
  * the whole thermostatted step -- what CudaVVKernels.cpp:144-185 + 670-754 do in 9-10 launches and
  * a blocking host round trip -- as ONE launch with a grid barrier (csrc/vvb200_resident.cuh).
  * mode: -1 = default (on unless the environment says VVB200_RESIDENT=0), 0 = always use the two

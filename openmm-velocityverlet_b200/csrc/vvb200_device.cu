@@ -109,6 +109,31 @@ struct NhcDevice {
     int numTG, nc, loops;
 };
 
+// ---- all-reduce of the reduction vector over NVLink peer memory ---------------------------------------------------
+// Multi-GPU runs (one process per GPU, particles partitioned by whole molecules) need ONE exchange per step: the sum
+// over ranks of <= 10 doubles.  No collective launch: the block that already holds this rank's final sums -- the LAST
+// block of pass A (lastBlockFinish), or the single block of nhc_peer_kernel on the paths that have no pass A --
+// stores the vector into a slot of every peer's exchange buffer (cudaIpc-mapped, plain st.global over NVLink),
+// publishes a sequence number with release semantics, waits for the other ranks' numbers with acquire loads, sums the
+// slots in rank order (=> bitwise identical on every rank) and goes on to the NH chains.  Slots are double-buffered
+// by step parity; a rank cannot run two steps ahead because it needs every peer's flag of the step in between.  The
+// sequence number lives in device memory and is advanced by the exchanging block itself, so a captured CUDA graph
+// replays correctly.  The wait is bounded (VVB200_PEER_TIMEOUT_S, default 30 s): on expiry the block raises a flag in
+// mapped host memory -- the next host call on the plan returns VVB200_ERR_CUDA -- and poisons the sums with NaN so that
+// no silently wrong trajectory continues; the GPU is never left hanging on a dead peer.
+#define VVB200_MAX_RANKS 8
+struct PeerSlots {
+    double data[2][VVB200_MAX_RANKS][16];
+    unsigned long long flag[2][VVB200_MAX_RANKS];
+};
+struct PeerCtx {
+    PeerSlots *buf[VVB200_MAX_RANKS];    // buf[r] = rank r's exchange buffer as mapped in this process
+    int rank, world;
+    unsigned long long timeoutNs;
+    unsigned long long *seq;             // device: exchanges done so far
+    volatile unsigned int *timedOut;     // mapped host memory: set when a wait expired
+};
+
 struct KParams {
     int N, paddedN, numTiles;
     const int4 *tileDesc;                      // 2 x int4 per tile, see vvb200_stream.cuh
@@ -151,6 +176,9 @@ struct KParams {
     int tileBegin, tileEnd, accumulateRed;
     int pdl;     // launch with programmatic stream serialization (host side only)
     unsigned int *gridGen;   // generation word of its grid barrier
+    // multi-GPU: pass A's last block exchanges the reduction vector with the peers before it advances the chains
+    int peerOn;
+    PeerCtx peer;
 };
 
 enum { KICK_NONE = 0, KICK_MIDDLE = 1, KICK_VV = 2 };
@@ -274,24 +302,6 @@ __global__ void nhc_kernel(NhcDevice *s, double dt) {
         nhcFinish<COS>(s, dt, threadIdx.x);
 }
 
-// ---- all-reduce of the reduction vector over NVLink peer memory, fused with the NH-chain update ----------------
-// Multi-GPU runs (one process per GPU, particles partitioned by whole molecules) need ONE exchange per step: the sum
-// over ranks of <= 10 doubles.  Instead of a separate NCCL launch, the single-block kernel that advances the chains
-// does it itself: every rank stores its vector into a slot of every peer's exchange buffer (cudaIpc-mapped, plain
-// st.global over NVLink), publishes a sequence number with release semantics, waits for the other ranks' numbers
-// with acquire loads, sums the slots in rank order (=> bitwise identical on every rank) and goes on to the chains.
-// Slots are double-buffered by step parity; a rank cannot run two steps ahead because it needs every peer's flag of
-// the step in between.  The wait is bounded (~2 s): on expiry the sums become NaN instead of hanging the GPU.
-#define VVB200_MAX_RANKS 8
-struct PeerSlots {
-    double data[2][VVB200_MAX_RANKS][16];
-    unsigned long long flag[2][VVB200_MAX_RANKS];
-};
-struct PeerCtx {
-    PeerSlots *buf[VVB200_MAX_RANKS];    // buf[r] = rank r's exchange buffer as mapped in this process
-    int rank, world;
-};
-
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -300,38 +310,60 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
-template <bool COS>
-__global__ void nhc_peer_kernel(NhcDevice *s, const PeerCtx ctx, unsigned long long seq, double dt) {
-    __shared__ int expired;
-    const int t = threadIdx.x, par = (int) (seq & 1);
-    if (t == 0) expired = 0;
-    __syncthreads();
-    if (t < ctx.world) {
-        // my vector into rank t's buffer, slot [parity][my rank]
-        double *dst = ctx.buf[t]->data[par][ctx.rank];
-        for (int k = 0; k < VVB200_NRED; k++)
-            dst[k] = s->red[k];
-        __threadfence_system();
-        st_release_sys(&ctx.buf[t]->flag[par][ctx.rank], seq);
-        // wait for rank t's vector in MY buffer
-        const unsigned long long *f = &ctx.buf[ctx.rank]->flag[par][t];
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) != seq) {
-            if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: a peer died; do not hang the device
-                expired = 1;
-                break;
-            }
-            __nanosleep(100);
+// First half of the exchange, by thread t < world of the exchanging block: my vector (`mine`, VVB200_NRED doubles in
+// shared or global memory) into rank t's buffer, then wait for rank t's vector in my own buffer.  Returns false when the
+// wait expired.  `seq` = number of this exchange (1, 2, ...), the same on every rank.
+__device__ __forceinline__ bool peerPublishAndWait(const PeerCtx &ctx, unsigned long long seq, const double *mine, int t) {
+    const int par = (int) (seq & 1);
+    double *dst = ctx.buf[t]->data[par][ctx.rank];
+    for (int k = 0; k < VVB200_NRED; k++)
+        dst[k] = mine[k];
+    __threadfence_system();
+    st_release_sys(&ctx.buf[t]->flag[par][ctx.rank], seq);
+    const unsigned long long *f = &ctx.buf[ctx.rank]->flag[par][t];
+    const unsigned long long t0 = globalTimerNs();
+    while (ld_acquire_sys(f) != seq) {
+        if (globalTimerNs() - t0 > ctx.timeoutNs) {      // a peer died or stalled: do not hang the device
+            *ctx.timedOut = 1u;
+            return false;
         }
+        __nanosleep(100);
+    }
+    return true;
+}
+// Second half, by thread t < VVB200_NRED after a block barrier: the sum over ranks in rank order
+__device__ __forceinline__ double peerSum(const PeerCtx &ctx, unsigned long long seq, int t, bool expired) {
+    const int par = (int) (seq & 1);
+    double v = 0;
+    for (int r = 0; r < ctx.world; r++)
+        v += __ldcg(&ctx.buf[ctx.rank]->data[par][r][t]);
+    return expired ? __longlong_as_double(0x7ff8000000000000LL) : v;
+}
+
+// Exchange + NH chains as a kernel of its own: the paths whose sums do not come out of pass A's last block (the
+// any-topology gather kernels, the chunked host pipeline)
+template <bool COS>
+__global__ void nhc_peer_kernel(NhcDevice *s, const PeerCtx ctx, double dt) {
+    __shared__ int expired;
+    __shared__ unsigned long long seqS;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        expired = 0;
+        seqS = ++*ctx.seq;
     }
     __syncthreads();
-    if (t < VVB200_NRED) {
-        double v = 0;
-        for (int r = 0; r < ctx.world; r++)
-            v += ctx.buf[ctx.rank]->data[par][r][t];
-        s->red[t] = expired ? __longlong_as_double(0x7ff8000000000000LL) : v;
-    }
+    const unsigned long long seq = seqS;
+    if (t < ctx.world && !peerPublishAndWait(ctx, seq, s->red, t))
+        expired = 1;
+    __syncthreads();
+    if (t < VVB200_NRED)
+        s->red[t] = peerSum(ctx, seq, t, expired != 0);
     __syncthreads();
     if (t < 3)
         nhcFinish<COS>(s, dt, t);
@@ -702,7 +734,7 @@ struct vvb200_device_state {
     PeerSlots *peerLocal = nullptr;
     PeerCtx peer{};
     bool peerAttached = false;
-    unsigned long long peerSeq = 0;
+    unsigned int *peerTimedOutHost = nullptr;     // mapped pinned host word the exchanging block raises on expiry
     std::vector<void *> peerMapped;
     void *oldDelta = nullptr;   // mixed4[N], plugin-owned like the reference's (CudaVVKernels.cpp:90-96)
     void *comV = nullptr, *comCbar = nullptr, *ldForce = nullptr;
@@ -767,6 +799,7 @@ void vvb200_device_free(vvb200_plan *plan) {
     if (d->sOut) cudaStreamDestroy(d->sOut);
     for (void *m : d->peerMapped)
         cudaIpcCloseMemHandle(m);
+    if (d->peerTimedOutHost) cudaFreeHost(d->peerTimedOutHost);
     delete d;
     plan->dev = nullptr;
 }
@@ -808,6 +841,10 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     p->dev = d;
     CUDA_TRY(cudaGetDevice(&d->device));
     CUDA_TRY(cudaDeviceGetAttribute(&d->numSM, cudaDevAttrMultiProcessorCount, d->device));
+    if (d->numSM != p->tileSM && !vvb200_build_tiles(p, d->numSM)) {     // tile sizes follow the device actually used
+        vvb200_set_error("vvb200_plan_upload: %s", p->tiledWhyNot.c_str());
+        return VVB200_ERR_UNSUPPORTED_TOPOLOGY;
+    }
     d->numTiles = (int) p->tileStart.size() - 1;
     d->pdl = envInt("VVB200_PDL", 1) ? 1 : 0;
 
@@ -901,6 +938,7 @@ extern "C" int vvb200_set_global_thermostat(vvb200_plan *p, const double *dof3, 
     }
     for (int g = 0; g < 3; g++) p->dofGlobal[g] = dof3[g];
     p->totalMassGlobal = totalMass;
+    p->partitioned = true;
     // temperature-group count follows the global DOFs (CudaVVKernels.cpp:567-573)
     p->numTempGroup = 3;
     if (p->dofGlobal[VVB200_TG_DRUDE] == 0) {
@@ -927,6 +965,11 @@ static int checkStepArgs(const vvb200_plan *p, const vvb200_buffers *b, const ch
         vvb200_set_error("%s: plan not uploaded (call vvb200_plan_upload)", who);
         return VVB200_ERR_NOT_UPLOADED;
     }
+    if (p->dev->peerTimedOutHost && *(volatile unsigned int *) p->dev->peerTimedOutHost) {
+        vvb200_set_error("%s: a multi-GPU peer exchange timed out in an earlier step (a rank died or stalled for longer than "
+                         "VVB200_PEER_TIMEOUT_S); velocities since then are NaN", who);
+        return VVB200_ERR_CUDA;
+    }
     if (!b->velm || (needPos && !b->posq) || (needForce && !b->force) ||
         (needPos && p->precision == VVB200_MIXED && !b->posq_correction)) {
         vvb200_set_error("%s: missing device buffer", who);
@@ -952,6 +995,8 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.N = p->N; k.paddedN = p->paddedN; k.numTiles = d->numTiles;
     k.tileBegin = 0; k.tileEnd = d->numTiles;
     k.pdl = d->pdl;
+    k.peerOn = 0;                 // set by the multi-GPU step calls when the peer exchange is attached
+    k.peer = d->peer;
     k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
     k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
@@ -1044,9 +1089,28 @@ static cudaError_t launchStreaming(void (*kernel)(Args...), int grid, int blockT
     return cudaLaunchKernelEx(&cfg, kernel, k);
 }
 
+// Launch configurations are cached per kernel instantiation AND per device: cudaFuncSetAttribute / occupancy belong to
+// the device that is current, and one process may hold OpenMM Contexts on several GPUs.
+#define VVB200_MAX_DEVICES 64
+struct CfgCache {
+    LaunchCfg cfg[VVB200_MAX_DEVICES];
+    bool valid[VVB200_MAX_DEVICES] = {};
+};
+static int currentDeviceSlot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < VVB200_MAX_DEVICES ? dev : 0;
+}
+
 template <int MODE, int KICK, bool EXTRA>
 static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
-    static LaunchCfg cfg = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA, KICK != KICK_NONE>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", passABlocks(KICK), BTHREADS, 8);
+    static CfgCache cache;
+    const int slot = currentDeviceSlot();
+    if (!cache.valid[slot]) {
+        cache.cfg[slot] = configure(kick_reduce_kernel<MODE, KICK, EXTRA>, smemBytesA<MODE, EXTRA, KICK != KICK_NONE>, "VVB200_STAGES_A", "VVB200_BLOCKS_A", passABlocks(KICK), BTHREADS, 8);
+        cache.valid[slot] = true;
+    }
+    const LaunchCfg &cfg = cache.cfg[slot];
     k.stagesA = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
     return launchStreaming(kick_reduce_kernel<MODE, KICK, EXTRA>, grid, BTHREADS, cfg.smem, st, k);
@@ -1057,7 +1121,13 @@ static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
     // the scale-only variant stages 36 B/particle instead of 68: it needs a deeper ring for the same bytes in flight
     constexpr int maxStages = VARIANT == VAR_SCALE_ONLY ? 8 : MAXSTAGES_B;
     constexpr int blockThreads = passBConsumers(VARIANT) + 32;
-    static LaunchCfg cfg = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", passBMinBlocks(VARIANT), blockThreads, maxStages);
+    static CfgCache cache;
+    const int slot = currentDeviceSlot();
+    if (!cache.valid[slot]) {
+        cache.cfg[slot] = configure(scale_drift_kernel<MODE, VARIANT, EXTRA>, smemBytesB<MODE, VARIANT, EXTRA>, "VVB200_STAGES_B", "VVB200_BLOCKS_B", passBMinBlocks(VARIANT), blockThreads, maxStages);
+        cache.valid[slot] = true;
+    }
+    const LaunchCfg &cfg = cache.cfg[slot];
     k.stagesB = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
     return launchStreaming(scale_drift_kernel<MODE, VARIANT, EXTRA>, grid, blockThreads, cfg.smem, st, k);
@@ -1099,7 +1169,11 @@ template <int MODE, int KICK, int VARIANT, bool EXTRA>
 static int launchResident(KParams k, int numSM, cudaStream_t st) {
     constexpr int MAXT = 8;
     auto kernel = resident_step_kernel<MODE, KICK, VARIANT, EXTRA>;
-    static int maxOptin = [&] {
+    // per device, like the streaming kernels' configurations
+    struct ResidentCache { int maxOptin = -1; int occ[MAXT + 1]; };
+    static ResidentCache caches[VVB200_MAX_DEVICES];
+    ResidentCache &rc = caches[currentDeviceSlot()];
+    if (rc.maxOptin < 0) {
         int dev = 0, v = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -1110,9 +1184,11 @@ static int launchResident(KParams k, int numSM, cudaStream_t st) {
             cudaGetLastError();
             v = 48 * 1024;
         }
-        return v;
-    }();
-    static int occCache[MAXT + 1] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+        rc.maxOptin = v;
+        for (int t = 0; t <= MAXT; t++) rc.occ[t] = -1;
+    }
+    const int maxOptin = rc.maxOptin;
+    int *occCache = rc.occ;
     auto smem = [](int T) { return smemBytesR<MODE, KICK, VARIANT, EXTRA>(T); };
     auto occ = [&](int T) {
         if (occCache[T] < 0) {
@@ -1135,7 +1211,7 @@ static int launchResident(KParams k, int numSM, cudaStream_t st) {
     k.tilesPerBlock = T;
     // Cooperative launch: the runtime places the whole grid or nothing, so two contexts stepping on different streams
     // of one GPU can never hold half of each other's blocks while both wait at their grid barriers.
-    static const int coop = envInt("VVB200_COOP", 1);
+    static const int coop = envInt("VVB200_COOP", 1);      // an environment switch, not device state
     if (coop) {
         void *args[] = {&k};
         return cudaLaunchCooperativeKernel((const void *) kernel, dim3(grid), dim3(CTHREADS), args, smem(T), st) == cudaSuccess ? 1 : -1;
@@ -1394,7 +1470,11 @@ extern "C" int vvb200_middle_kick_reduce(vvb200_plan *p, const vvb200_buffers *b
         return hasNH(p) ? generalThermostat(p, &bb, a, true, false, false, st) : VVB200_OK;
     }
     KParams k = makeParams(p, b, a);
-    k.fuseNHC = 0;
+    // peers attached: the last block of this launch exchanges the sums over NVLink and advances the chains itself, and
+    // vvb200_middle_nhc_scale_drift is pass B alone.  Otherwise the sums stay in vvb200_partials_ptr() for the caller's
+    // all-reduce.
+    k.peerOn = p->dev->peerAttached ? 1 : 0;
+    k.fuseNHC = k.peerOn;
     profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, p->par.cos_acceleration != 0, k, p->dev->numSM, st)));
     p->launches++;
@@ -1406,11 +1486,10 @@ static int launchNhc(vvb200_plan *p, cudaStream_t st) {
     vvb200_device_state *d = p->dev;
     if (d->peerAttached) {
         // all-reduce over peer memory + NH chains in one single-block kernel (no NCCL launch)
-        const unsigned long long seq = ++d->peerSeq;
         if (p->par.cos_acceleration != 0)
-            nhc_peer_kernel<true><<<1, 32, 0, st>>>(d->nhc, d->peer, seq, p->par.step_size);
+            nhc_peer_kernel<true><<<1, 32, 0, st>>>(d->nhc, d->peer, p->par.step_size);
         else
-            nhc_peer_kernel<false><<<1, 32, 0, st>>>(d->nhc, d->peer, seq, p->par.step_size);
+            nhc_peer_kernel<false><<<1, 32, 0, st>>>(d->nhc, d->peer, p->par.step_size);
         p->launches++;
         CUDA_TRY(cudaGetLastError());
         return VVB200_OK;
@@ -1428,7 +1507,10 @@ extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffer
     int rc = checkStepArgs(p, b, "vvb200_middle_nhc_scale_drift", true, false);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t) stream;
-    if (hasNH(p) && (rc = launchNhc(p, st))) return rc;
+    // The exchange (when peers are attached) and the chains already ran inside pass A on the tiled path.  A partition
+    // without thermostat particles still takes part in the exchange: its peers wait for its (zero) vector.
+    const bool exchangeHere = !(p->tiled && p->dev->peerAttached);
+    if (exchangeHere && (hasNH(p) || p->partitioned) && (rc = launchNhc(p, st))) return rc;
     if (!p->tiled) {
         vvb200_buffers bb;
         if ((rc = withPosDelta(p, b, &bb, st))) return rc;
@@ -1469,7 +1551,9 @@ extern "C" int vvb200_peer_attach(vvb200_plan *p, int rank, int world, const voi
         return VVB200_ERR_INVALID_ARGUMENT;
     }
     vvb200_device_state *d = p->dev;
+    unsigned long long *keepSeq = d->peer.seq;
     memset(&d->peer, 0, sizeof d->peer);
+    d->peer.seq = keepSeq;
     d->peer.rank = rank;
     d->peer.world = world;
     for (int r = 0; r < world; r++) {
@@ -1484,7 +1568,20 @@ extern "C" int vvb200_peer_attach(vvb200_plan *p, int rank, int world, const voi
         d->peerMapped.push_back(mapped);
         d->peer.buf[r] = (PeerSlots *) mapped;
     }
-    d->peerSeq = 0;
+    if (!d->peer.seq) {
+        unsigned long long *seq = nullptr;
+        CUDA_TRY(cudaMalloc((void **) &seq, sizeof *seq));
+        d->allocations.push_back(seq);
+        d->peer.seq = seq;
+    }
+    CUDA_TRY(cudaMemset(d->peer.seq, 0, sizeof(unsigned long long)));
+    if (!d->peerTimedOutHost)
+        CUDA_TRY(cudaHostAlloc((void **) &d->peerTimedOutHost, sizeof(unsigned int), cudaHostAllocMapped));
+    *d->peerTimedOutHost = 0;
+    void *flagDev = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&flagDev, d->peerTimedOutHost, 0));
+    d->peer.timedOut = (volatile unsigned int *) flagDev;
+    d->peer.timeoutNs = (unsigned long long) std::max(1, envInt("VVB200_PEER_TIMEOUT_S", 30)) * 1000000000ull;
     d->peerAttached = world > 1;
     return VVB200_OK;
 }
@@ -1499,11 +1596,17 @@ extern "C" int vvb200_partials_ptr(vvb200_plan *p, void **ptr, int32_t *n) {
     return VVB200_OK;
 }
 
+extern "C" int vvb200_middle_nhc_scale_drift(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream);
+
 extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const vvb200_step_args *a, void *stream) {
     int rc = checkStepArgs(p, b, "vvb200_step_middle", true, true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t) stream;
     const bool cosine = p->par.cos_acceleration != 0;
+    if (!p->tiled && p->dev->peerAttached) {      // any topology on several GPUs: the split calls carry the exchange
+        if ((rc = vvb200_middle_kick_reduce(p, b, a, stream))) return rc;
+        return vvb200_middle_nhc_scale_drift(p, b, a, stream);
+    }
     if (!p->particlesLD.empty() && (rc = launchLangevin(p, b, a, st))) return rc;
     if (!p->tiled) {
         // any topology: kick | posDelta = dt/2 v | thermostat (gather kernels, NH chains on the device) |
@@ -1518,9 +1621,13 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
     }
     KParams k = makeParams(p, b, a);
     k.fuseNHC = hasNH(p);
+    if (p->dev->peerAttached) {      // molecule-partitioned multi-GPU run: see vvb200_middle_kick_reduce
+        k.peerOn = 1;
+        k.fuseNHC = 1;
+    }
     profMark(p->dev, 0, st);
     bool resident = false;
-    if ((rc = tryResident<KICK_MIDDLE, VAR_MIDDLE>(p, k, hasNH(p), st, &resident))) return rc;
+    if (!k.peerOn && (rc = tryResident<KICK_MIDDLE, VAR_MIDDLE>(p, k, hasNH(p), st, &resident))) return rc;
     if (resident) {   // small system: the whole step ran as one launch; reported as "pass A", pass B = 0
         profMark(p->dev, 1, st);
         profMark(p->dev, 2, st);
@@ -1987,7 +2094,9 @@ extern "C" int vvb200_measure_temperatures(vvb200_plan *p, const vvb200_buffers 
     }
     memset(out, 0, sizeof *out);
     out->num_temp_groups = p->numTempGroup;
-    for (int g = 0; g < 3; g++) out->dof[g] = p->dofGlobal[g];
+    // this plan's own particles: its DOFs and its mass (a molecule-partitioned run reports per partition; the caller
+    // all-reduces ke2 and dof for the whole box)
+    for (int g = 0; g < 3; g++) out->dof[g] = p->dof[g];
     if (!hasNH(p))
         return VVB200_OK;
     cudaStream_t st = (cudaStream_t) stream;
@@ -2003,7 +2112,7 @@ extern "C" int vvb200_measure_temperatures(vvb200_plan *p, const vvb200_buffers 
     double red[VVB200_NRED];
     CUDA_TRY(cudaMemcpyAsync(red, p->dev->nhc->red, sizeof red, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    const double V = cosine ? red[3] * (1.0 / p->totalMassGlobal) : 0.0;   // nhcFinish's expression
+    const double V = cosine ? red[3] * p->invMassTotal : 0.0;              // nhcFinish's expression on this plan's mass
     out->velocity_bias = V;
     for (int g = 0; g < p->numTempGroup; g++) {
         double ke2 = red[g];
@@ -2107,7 +2216,7 @@ static int stepHostPipelined(vvb200_plan *p, const vvb200_buffers *hb, const vvb
     }
     if (phase == 1)
         return VVB200_OK;
-    if (phase == 2 && hasNH(p)) {
+    if (phase == 2 && (hasNH(p) || p->partitioned)) {
         int rc = launchNhc(p, st);      // all-reduce over NVLink peer memory (when attached) + NH chains
         if (rc) return rc;
     }

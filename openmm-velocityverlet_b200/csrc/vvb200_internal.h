@@ -72,8 +72,10 @@ struct vvb200_plan {
     // global-thermostat overrides for molecule-partitioned multi-GPU runs
     double dofGlobal[3] = {0, 0, 0};
     double totalMassGlobal = 0;
+    bool partitioned = false;                   // vvb200_set_global_thermostat was called: one rank of a multi-GPU run
 
     // fused-path tables
+    int tileSM = 148;                           // multiprocessor count the tile sizes were chosen for
     bool tiled = false;
     std::string tiledWhyNot;
     std::vector<int32_t> tileStart;             // [numTiles+1]
@@ -95,6 +97,7 @@ struct vvb200_plan {
 };
 
 void vvb200_set_error(const char *fmt, ...);
+bool vvb200_build_tiles(vvb200_plan *plan, int numSM);
 void vvb200_device_free(vvb200_plan *plan);
 
 #endif

@@ -312,18 +312,26 @@ extern "C" int vvb200_plan_create(const vvb200_system *sys, const vvb200_params 
     p->invMassTotal = 1.0 / massTotal;
     p->totalMassGlobal = massTotal;
 
-    p->tiled = buildTiles(p);
-    if (p->tiled && getenv("VVB200_FORCE_GENERAL")) {     // testing hook: exercise the any-topology path
-        p->tiled = false;
-        p->tiledWhyNot = "forced by VVB200_FORCE_GENERAL";
-    }
-    if (!p->tiled && !buildPlainTiles(p)) {
+    if (!vvb200_build_tiles(p, p->tileSM)) {
         vvb200_set_error("vvb200_plan_create: %s", p->tiledWhyNot.c_str());
         delete p;
         return VVB200_ERR_UNSUPPORTED_TOPOLOGY;
     }
     *out = p;
     return VVB200_OK;
+}
+
+// (Re)builds the tile tables for a GPU with `numSM` multiprocessors: plan_create assumes a B200 (148); plan_upload
+// calls this again when the device it uploads to reports another count (tile sizes of small systems follow the number of
+// co-resident blocks).  False: no tiling of either kind exists (tiledWhyNot says why).
+bool vvb200_build_tiles(vvb200_plan *p, int numSM) {
+    p->tileSM = numSM > 0 ? numSM : 148;
+    p->tiled = buildTiles(p);
+    if (p->tiled && getenv("VVB200_FORCE_GENERAL")) {     // testing hook: exercise the any-topology path
+        p->tiled = false;
+        p->tiledWhyNot = "forced by VVB200_FORCE_GENERAL";
+    }
+    return p->tiled || buildPlainTiles(p);
 }
 
 // Tables of the fused two-pass kernels.  A tile is a contiguous particle range of at most
@@ -436,12 +444,12 @@ static bool buildTiles(vvb200_plan *p) {
 
     // Tile size.  Large systems: VVB200_TILE_CAP (what the streaming kernels' stages hold).  Small systems are bound
     // by the latency of each thread's dependent fp64 chain, not by bytes, so they are cut into more, smaller tiles --
-    // about one per co-resident block of the B200 (148 SMs x 2) -- which spreads the same work over more SMs.
+    // about one per co-resident block of the GPU (2 per SM; 148 SMs on a B200) -- which spreads the same work over more SMs.
     int cap = VVB200_TILE_CAP;
     {
         const char *env = getenv("VVB200_SMALL_TILES");
         if (!env || atoi(env) != 0) {
-            const int perBlock = (N + 2 * 148 - 1) / (2 * 148);
+            const int perBlock = (N + 2 * p->tileSM - 1) / (2 * p->tileSM);
             cap = std::min(VVB200_TILE_CAP, std::max(128, (perBlock + 31) / 32 * 32));
         }
     }
@@ -475,7 +483,7 @@ static bool buildTiles(vvb200_plan *p) {
         }
         // small tiles only pay while every tile still gets its own co-resident block (units that may not be split
         // leave tiles partly empty, so the count can exceed N / cap): otherwise grow the tile and cut again
-        if (ok && cap < VVB200_TILE_CAP && (int) p->tileStart.size() - 1 > 2 * 148) {
+        if (ok && cap < VVB200_TILE_CAP && (int) p->tileStart.size() - 1 > 2 * p->tileSM) {
             cap += 32;
             continue;
         }

@@ -119,6 +119,7 @@ template <int MODE, bool EXTRA> struct ScratchA {
     typedef typename Prec<MODE>::mixed mixed;
     PublishedA<MODE, EXTRA> pub[2];
     double red[CTHREADS / 32][VVB200_NRED];
+    unsigned long long peerSeq;
     unsigned int ticket;
 };
 
@@ -517,7 +518,9 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
     }
     // molecules cut across tiles: add their fragments up in tile order, finish the centre of mass the way phase 2 does
     // for whole molecules (drudeNoseHoover.cu:11-30, 91-97) and move M|V|^2 from the atom group to the molecular group
-    for (int k = tid; k < (p.kickOnly ? 0 : p.numSplit); k += CTHREADS) {
+    // (a step cut into several launches over tile ranges -- the host pipeline -- finishes them once, in the launch that
+    // covers the last tiles: by then every fragment has been written, and the M|V|^2 transfer is not added per launch)
+    for (int k = tid; k < (p.kickOnly || p.tileEnd != p.numTiles ? 0 : p.numSplit); k += CTHREADS) {
         mixed sx = 0, sy = 0, sz = 0, comMass = 0, sc = 0;
         for (int f = p.splitFragOffset[k]; f < p.splitFragOffset[k + 1]; f++) {
             const double *fp = p.fragPartials + 5 * (size_t) p.splitFragList[f];
@@ -560,6 +563,26 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
     if (tid == 0)
         *p.counter = 0;
     consumerBarrier();
+    if (p.peerOn) {
+        // multi-GPU: this rank's sums are final -- exchange them with the peers over NVLink right here (device.cu,
+        // "all-reduce of the reduction vector over NVLink peer memory"): no separate launch, and pass B still overlaps
+        // its prologue with this block through PDL
+        if (tid == 0) {
+            sm.ticket = 0;                                   // reused as the "a wait expired" mark
+            sm.peerSeq = ++*p.peer.seq;
+        }
+        consumerBarrier();
+        const unsigned long long seq = sm.peerSeq;
+        if (tid < p.peer.world && !peerPublishAndWait(p.peer, seq, sm.red[0], tid))
+            sm.ticket = 1;
+        consumerBarrier();
+        if (tid < VVB200_NRED) {
+            const double v = peerSum(p.peer, seq, tid, sm.ticket != 0);
+            work->red[tid] = v;
+            sm.red[0][tid] = v;
+        }
+        consumerBarrier();
+    }
 #ifdef VVB200_TRACE
     traceMark(7);
 #endif

@@ -1,8 +1,9 @@
 """Molecule-partitioned multi-GPU stepping: one process per GPU, each rank owns a contiguous
 range of WHOLE molecules (so Drude pairs, constraints and molecular centres of mass never cross ranks) with its
 slice of posq / velm / force.  The only exchange per step is one all-reduce (sum, fp64) of the <= 10-element
-reduction vector between the two passes; the Nose-Hoover chains are then advanced redundantly on every rank
-(deterministic fp64 => identical scale factors everywhere).
+reduction vector between the two passes -- done by the last block of pass A itself over NVLink peer memory, or by one
+NCCL all-reduce where the ranks cannot map each other's memory; the Nose-Hoover chains are then advanced redundantly
+on every rank (deterministic fp64 => identical scale factors everywhere).
 
 torch.distributed is only the plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
 import dataclasses
@@ -104,7 +105,8 @@ class DistributedPlan:
         self.plan.middle_kick_reduce(bufs, **kw)
         if not self.peer and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self._red, group=self.group)           # NCCL: the only exchange, <= 10 doubles
-        # peer path: the exchange happens inside the single-block NH-chain kernel, over cudaIpc-mapped NVLink memory
+        # peer path: the LAST BLOCK OF PASS A exchanged the sums over cudaIpc-mapped NVLink memory and advanced the chains;
+        # what follows is pass B alone -- the same two launches per step as on one GPU
         self.plan.middle_nhc_scale_drift(bufs, **kw)
 
     def step_host(self, host_state, **kw):

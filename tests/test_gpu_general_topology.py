@@ -178,3 +178,31 @@ def test_long_molecules_fused_equals_any_topology_path(vv, vo, monkeypatch):
         torch.cuda.synchronize()
         out.append(1e3 * e0.elapsed_time(e1) / 50)
     print(f"polymer melt {n} particles: fused {out[0]:.1f} us/step, any-topology path {out[1]:.1f} us/step")
+
+
+@pytest.mark.parametrize("cos", [False, True])
+def test_long_molecules_through_the_chunked_host_pipeline(vv, vo, monkeypatch, cos):
+    """vvb200_step_host cuts a step of a large system into tile ranges (copy-in / pass A / pass B / copy-out overlapped).
+    With thermostat molecules longer than a tile the fragments of one molecule can land in different ranges: the
+    centre-of-mass finish of the cut molecules (and the M|V|^2 transfer between the atom and molecular groups) must run
+    ONCE, in the launch that covers the last tiles -- not once per range on partly written fragment sums."""
+    monkeypatch.setenv("VVB200_HOST_PIPELINE_MIN", "1000")
+    monkeypatch.setenv("VVB200_HOST_CHUNKS", "7")
+    spec = vv.make_polymer(4, 900, 30, adjacent=True)
+    params = vv.Params(max_drude_distance=0.02, cos_acceleration=0.02 if cos else 0.0).resolved_for(spec)
+    host = vv.make_state(spec, "mixed")
+    inv_box_z = 1.0 / host.box[2] if cos else 0.0
+    p1, p2 = vv.Plan(spec, params, "mixed").upload(), vv.Plan(spec, params, "mixed").upload()
+    assert p1.tiled and p1.int_array("splitMolId").size > 0
+    p1.set_resident_mode(0)
+    bufs = vv.DeviceBuffers(host)
+    got = host.copy()
+    for _ in range(3):
+        p1.step(bufs, steps=1, inv_box_z=inv_box_z)
+        p2.step_host(got, steps=1, inv_box_z=inv_box_z)
+    want = bufs.to_host()
+    assert p2.launch_count > 3 * 2            # really chunked
+    n = spec.n
+    assert rel_err(got.velm[:n, :3], want.velm[:n, :3]) <= 1e-11 and rel_err(got.positions()[:n], want.positions()[:n]) <= 1e-11
+    a, b = p1.thermostat_state(), p2.thermostat_state()
+    assert rel_err(b["ke2"], a["ke2"]) <= 1e-12 and rel_err(b["vscale"], a["vscale"]) <= 1e-12
