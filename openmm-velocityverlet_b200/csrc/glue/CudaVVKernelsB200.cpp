@@ -12,7 +12,7 @@
 //   calc/remove/restoreVelocityBias, scaleVelocity                no-ops: folded into the step
 //   secondIntegrate                                               vvb200_step_middle  (kick + reductions + NH chains +
 //                                                                 scale + drift + hard wall + image mirror)
-//   updateImagePositions                                          no-op (done by vvb200_step_middle)
+//   updateImagePositions                                          no-op (done by whichever call wrote the positions)
 // With constraints or virtual sites OpenMM's solvers must run between the sub-steps, so the split entry points are
 // used: kick -> applyVelocityConstraints | (no-op) | thermostat_delta -> applyConstraints -> finish  (440 B/particle).
 // Velocity-Verlet scheme: thermostat | vv_kick(+posDelta) -> applyConstraints -> vv_positions | vv_kick | thermostat.
@@ -71,12 +71,28 @@ static vvb200_step_args stepArgs(CudaContext &cu, const VVB200Shared &sh, const 
     return a;
 }
 
-static void syncStepSize(VVB200Shared &sh, const VVIntegrator &integrator) {
-    // the reference re-reads the step size every step (CudaVVKernels.cpp:137-141)
-    if (integrator.getStepSize() != sh.stepSize) {
-        sh.stepSize = integrator.getStepSize();
-        VVB200_CHECK(vvb200_set_step_size(sh.plan, sh.stepSize));
+static void syncStepSize(CudaContext &cu, VVB200Shared &sh, const VVIntegrator &integrator) {
+    // The reference re-reads the step size every step and keeps OpenMM's own copy current: setNextStepSize in the middle
+    // scheme (CudaVVKernels.cpp:137-141), an upload of (0, dt) into integration.getStepSize() in the velocity-Verlet
+    // scheme (:309-319).  Other OpenMM code reads that array (time-shifted kinetic energy, constraint kernels), so it is
+    // kept in step here too, although the vvb200 kernels take dt as a parameter.
+    const double stepSize = integrator.getStepSize();
+    if (stepSize == sh.stepSize && sh.stepSizePublished)
+        return;
+    CudaIntegrationUtilities &integration = cu.getIntegrationUtilities();
+    if (integrator.getUseMiddleScheme()) {
+        integration.setNextStepSize(stepSize);
+    } else if (cu.getUseDoublePrecision() || cu.getUseMixedPrecision()) {
+        double2 ss = make_double2(0, stepSize);
+        integration.getStepSize().upload(&ss);
+    } else {
+        float2 ss = make_float2(0, (float) stepSize);
+        integration.getStepSize().upload(&ss);
     }
+    if (stepSize != sh.stepSize)
+        VVB200_CHECK(vvb200_set_step_size(sh.plan, stepSize));
+    sh.stepSize = stepSize;
+    sh.stepSizePublished = true;
 }
 
 // What makes two particles different for THIS plugin.  CudaContext::reorderAtoms only ever swaps molecules all of whose
@@ -105,10 +121,14 @@ private:
 static void createPlan(VVB200Shared &sh, CudaContext &cu, const System &system, const VVIntegrator &integrator,
                        const DrudeForce *force) {
     ContextSelector selector(cu);
+    // BEFORE initializeContexts: that call is what runs CudaContext::initialize() -> findMoleculeGroups(), the only
+    // consumer of ForceInfos.  Registered afterwards it would never be consulted and molecules with different plugin
+    // roles could still be swapped by reorderAtoms.  (It needs the System and the integrator's lists, not the plan.)
+    const int n = system.getNumParticles();
+    cu.addForce(new VVB200ForceInfo(n, integrator));     // owned by the context, like every ForceInfo
     cu.getPlatformData().initializeContexts(system);
     cu.getIntegrationUtilities().initRandomNumberGenerator((unsigned int) integrator.getRandomNumberSeed());
 
-    const int n = system.getNumParticles();
     vector<double> masses(n);
     vector<int32_t> molId(n);
     bool virtualSites = false;
@@ -181,7 +201,6 @@ static void createPlan(VVB200Shared &sh, CudaContext &cu, const System &system, 
     const int precision = cu.getUseDoublePrecision() ? VVB200_DOUBLE : cu.getUseMixedPrecision() ? VVB200_MIXED : VVB200_SINGLE;
     VVB200_CHECK(vvb200_plan_create(&s, &par, precision, &sh.plan));     // reference's exception texts on conflicts
     VVB200_CHECK(vvb200_plan_upload(sh.plan, cu.getCurrentStream()));
-    cu.addForce(new VVB200ForceInfo(n, integrator));     // owned by the context, like every ForceInfo
     sh.constrained = system.getNumConstraints() > 0 || virtualSites;
     sh.hasNH = !integrator.getParticlesNH().empty();
     sh.stepSize = par.step_size;
@@ -209,7 +228,7 @@ void CudaIntegrateMiddleStepKernel::resetExtraForce(ContextImpl &, const VVInteg
 
 void CudaIntegrateMiddleStepKernel::firstIntegrate(ContextImpl &, const VVIntegrator &integrator) {
     ContextSelector selector(cu);
-    syncStepSize(*sh, integrator);
+    syncStepSize(cu, *sh, integrator);
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);
     if (!sh->constrained)
@@ -251,7 +270,7 @@ void CudaIntegrateVVStepKernel::resetExtraForce(ContextImpl &, const VVIntegrato
 
 void CudaIntegrateVVStepKernel::firstIntegrate(ContextImpl &, const VVIntegrator &integrator) {
     ContextSelector selector(cu);
-    syncStepSize(*sh, integrator);
+    syncStepSize(cu, *sh, integrator);
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);
     CudaIntegrationUtilities &integration = cu.getIntegrationUtilities();
@@ -305,12 +324,9 @@ void CudaModifyImageChargeKernel::initialize(const System &, const VVIntegrator 
     sh = VVB200Shared::get(cu, false);
 }
 
-void CudaModifyImageChargeKernel::updateImagePositions(ContextImpl &, const VVIntegrator &integrator) {
-    if (integrator.getUseMiddleScheme() && !sh->constrained)
-        return;                             // vvb200_step_middle already mirrored the images
-    ContextSelector selector(cu);
-    vvb200_buffers b = deviceBuffers(cu);
-    VVB200_CHECK(vvb200_update_image_positions(sh->plan, &b, cu.getCurrentStream()));
+void CudaModifyImageChargeKernel::updateImagePositions(ContextImpl &, const VVIntegrator &) {
+    // nothing left to do: every call that writes positions -- vvb200_step_middle, vvb200_middle_finish,
+    // vvb200_vv_positions -- already mirrored the images of the particles it moved (include/vvb200.h)
 }
 
 // ---- electric field / cosine acceleration: forces are evaluated inside the kick ----------------------------------------

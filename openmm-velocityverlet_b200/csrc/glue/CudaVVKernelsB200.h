@@ -22,6 +22,7 @@ struct VVB200Shared {
     bool hasNH = false;
     unsigned int randomIndex = 0; // what prepareRandomNumbers returned this step
     double stepSize = -1.0;
+    bool stepSizePublished = false;   // OpenMM's own step-size array holds stepSize
     ~VVB200Shared() { vvb200_plan_destroy(plan); }
     static std::shared_ptr<VVB200Shared> get(CudaContext &cu, bool create);
 };

@@ -58,7 +58,9 @@ class SystemSpec:
             self.mol_id = _i32(mol_id)
             self.n_mol = int(self.mol_id.max()) + 1
         else:
-            self.mol_id, self.n_mol = molecules_from_bonds(self.n, self.bonds)
+            # ContextImpl::getMolecules [OMM-mem]: every force's bonded pairs (DrudeForce: Drude-parent) AND the constraints
+            links = np.concatenate([self.bonds, self.drude_pairs, self.constraints]) if self.n else self.bonds
+            self.mol_id, self.n_mol = molecules_from_bonds(self.n, links)
         return self
 
     def c_arrays(self):

@@ -443,3 +443,190 @@ class Reference:
         out = np.zeros((self.n_mol, 4), dtype=mixed)
         self.lib.vvref_get_com_velm(self.h, _ptr(out))
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference plugin's OWN host code (and the B200 glue) running under the mini-OpenMM
+# (oracle/mini_openmm; libraries oracle/_ref/libvvplugin_{ref_cpu,ref_cuda,glue_cuda}_<mode>.so)
+# ---------------------------------------------------------------------------------------------
+class _MommSystem(C.Structure):
+    _fields_ = [("numParticles", C.c_int32), ("masses", C.c_void_p),
+                ("numBonds", C.c_int32), ("bonds", C.c_void_p),
+                ("numDrude", C.c_int32), ("drudePairs", C.c_void_p),
+                ("numConstraints", C.c_int32), ("constraints", C.c_void_p), ("constraintDistances", C.c_void_p),
+                ("hasCMMotionRemover", C.c_int32), ("numDrudeForces", C.c_int32),
+                ("numLD", C.c_int32), ("particlesLD", C.c_void_p),
+                ("numImagePairs", C.c_int32), ("imagePairs", C.c_void_p),
+                ("numElectrolyte", C.c_int32), ("particlesElectrolyte", C.c_void_p)]
+
+
+class _MommParams(C.Structure):
+    _fields_ = [("temperature", C.c_double), ("frequency", C.c_double), ("drudeTemperature", C.c_double),
+                ("drudeFrequency", C.c_double), ("stepSize", C.c_double),
+                ("numNHChains", C.c_int32), ("loopsPerStep", C.c_int32),
+                ("useCOMTempGroup", C.c_int32), ("useMiddleScheme", C.c_int32),
+                ("maxDrudeDistance", C.c_double), ("friction", C.c_double), ("drudeFriction", C.c_double),
+                ("mirrorLocation", C.c_double), ("electricField", C.c_double), ("cosAcceleration", C.c_double),
+                ("randomNumberSeed", C.c_int32), ("debug", C.c_int32)]
+
+
+def plugin_lib_path(flavour, mode):
+    return os.path.join(HERE, "_ref", f"libvvplugin_{flavour}_{mode}.so")
+
+
+def plugin_available(flavour="ref_cpu", mode="mixed"):
+    return os.path.exists(plugin_lib_path(flavour, mode))
+
+
+_plugin_libs = {}
+
+
+def plugin_lib(flavour, mode):
+    key = (flavour, mode)
+    if key not in _plugin_libs:
+        lib = C.CDLL(plugin_lib_path(flavour, mode))      # RTLD_LOCAL: every flavour keeps its own Platform registry
+        lib.momm_last_error.restype = C.c_char_p
+        lib.momm_create.restype = C.c_void_p
+        lib.momm_create.argtypes = [C.POINTER(_MommSystem), C.POINTER(_MommParams), C.c_void_p]
+        lib.momm_destroy.argtypes = [C.c_void_p]
+        lib.momm_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        lib.momm_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.momm_array_pointers.argtypes = [C.c_void_p, C.c_void_p]
+        lib.momm_set_constraint_standin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.momm_step.argtypes = [C.c_void_p, C.c_int]
+        lib.momm_set_step_size.argtypes = [C.c_void_p, C.c_double]
+        lib.momm_get_upload.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        lib.momm_get_int_list.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        lib.momm_get_f64.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.momm_get_viscosity.argtypes = [C.c_void_p, C.c_void_p]
+        lib.momm_counters.argtypes = [C.c_void_p, C.c_void_p]
+        lib.momm_particles_identical.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _plugin_libs[key] = lib
+    return _plugin_libs[key]
+
+
+class PluginError(RuntimeError):
+    """an OpenMMException thrown by the reference's (or the glue's) code"""
+
+
+class MiniContext:
+    """An OpenMM::Context holding the reference's OWN VVIntegrator (openmmapi/src/VVIntegrator.cpp, compiled unchanged)
+    under the mini-OpenMM.  flavour: "ref_cpu" / "ref_cuda" = the reference's own CudaVVKernels.cpp + kernel sources
+    (host memory + SIMT shim, or device memory + real launches); "glue_cuda" = csrc/glue/CudaVVKernelsB200.cpp over
+    libvvb200.so.  step() is VVIntegrator::step(): the reference's stepMiddle / stepVV make the virtual calls.
+    auto=True leaves useCOMTempGroup / friction to VVIntegrator::initialize's own auto rules."""
+
+    F64 = {"moleculeMasses": 0, "moleculeInvMasses": 1, "dof": 2, "etaMass": 3, "NkbT": 4, "ke2": 5, "vscale": 6,
+           "eta": 7, "etaDot": 8, "etaDotDot": 9, "invMassTotal": 10, "settings": 11}
+    INT = {"particlesNH": 0, "moleculesNH": 1, "particleMolId": 2, "particlesLD": 3, "electrolyte": 4}
+    # CudaArray names in the reference's initialize() methods (CudaVVKernels.cpp:76, 598-604, 806-807, 889, 955)
+    UPLOADS = {"drudePairs": "vvDrudePairs", "particlesNH": "particlesNH", "moleculesNH": "moleculesNH",
+               "normalNH": "normalParticlesNH", "pairsNH": "pairParticlesNH", "particleMolId": "particleMolId",
+               "particlesInMolecules": "particlesInMolecules", "sortedByMol": "particlesSortedByMolId",
+               "normalLD": "normalParticlesLD", "pairsLD": "drudePairParticlesLD", "imagePairs": "imagePairs",
+               "electrolyte": "particlesElectrolyte"}
+
+    def __init__(self, spec, params, precision="mixed", flavour="ref_cpu", auto=False, stream=0, num_drude_forces=-1,
+                 constraint_distances=None):
+        self.lib = plugin_lib(flavour, precision)
+        self.spec, self.params, self.precision, self.flavour = spec, params, precision, flavour
+        k = self._keep = spec.c_arrays()
+        bonds = np.ascontiguousarray(spec.bonds, dtype=np.int32)
+        dist = None if constraint_distances is None else np.ascontiguousarray(constraint_distances, dtype=np.float64)
+        self._keep2 = (bonds, dist)
+        s = _MommSystem(spec.n, _ptr(k["masses"]), bonds.shape[0], _ptr(bonds), spec.drude_pairs.shape[0], _ptr(k["drude_pairs"]),
+                        spec.constraints.shape[0], _ptr(k["constraints"]), _ptr(dist), int(spec.has_cmm), num_drude_forces,
+                        spec.langevin.shape[0], _ptr(k["langevin"]), spec.image_pairs.shape[0], _ptr(k["image_pairs"]),
+                        spec.electrolyte.shape[0], _ptr(k["electrolyte"]))
+        p = _MommParams(params.temperature, params.frequency, params.drude_temperature, params.drude_frequency, params.step_size,
+                        params.num_nh_chains, params.loops_per_step, -1 if auto else int(params.use_com_temp_group),
+                        int(params.use_middle_scheme), params.max_drude_distance, -1.0 if auto else params.friction,
+                        -1.0 if auto else params.drude_friction, params.mirror_location, params.electric_field,
+                        params.cos_acceleration, 0, 0)
+        self.h = self.lib.momm_create(C.byref(s), C.byref(p), C.c_void_p(stream))
+        if not self.h:
+            raise PluginError(self.lib.momm_last_error().decode())
+        self._shape = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.momm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise PluginError(self.lib.momm_last_error().decode())
+
+    def set_state(self, state):
+        self._state0 = state
+        box = np.array(state.box, dtype=np.float64)
+        self._ok(self.lib.momm_set_state(self.h, _ptr(state.posq), _ptr(state.corr) if state.corr is not None else None,
+                                         _ptr(state.velm), _ptr(state.force), _ptr(state.random), state.random.shape[0],
+                                         _ptr(box)))
+        return self
+
+    def get_state(self):
+        s = self._state0.copy()
+        self._ok(self.lib.momm_get_state(self.h, _ptr(s.posq), _ptr(s.corr) if s.corr is not None else None, _ptr(s.velm)))
+        return s
+
+    def set_constraints(self, standin):
+        if standin is None:
+            self.lib.momm_set_constraint_standin(self.h, 0, None, None, None, 0)
+        else:
+            self._standin = standin
+            self.lib.momm_set_constraint_standin(self.h, *standin.c_args())
+        return self
+
+    def step(self, steps=1):
+        self._ok(self.lib.momm_step(self.h, steps))
+
+    def set_step_size(self, dt):
+        self.lib.momm_set_step_size(self.h, dt)
+
+    def upload(self, name):
+        """int32 view of the last upload to the reference CudaArray behind `name` (None if it was never uploaded)"""
+        p, n, e = C.c_void_p(), C.c_int64(), C.c_int32()
+        if self.lib.momm_get_upload(self.h, self.UPLOADS.get(name, name).encode(), C.byref(p), C.byref(n), C.byref(e)) != 0:
+            return None
+        return np.frombuffer(C.string_at(p, n.value), dtype=np.int32).copy()
+
+    def int_list(self, name):
+        p, n = C.c_void_p(), C.c_int64()
+        assert self.lib.momm_get_int_list(self.h, self.INT[name], C.byref(p), C.byref(n)) == 0
+        return np.frombuffer(C.string_at(p, 4 * n.value), dtype=np.int32).copy()
+
+    def f64(self, name, cap=1 << 22):
+        cap = min(cap, max(64, self.spec.n_mol + 8))
+        out = np.zeros(cap, dtype=np.float64)
+        n = self.lib.momm_get_f64(self.h, self.F64[name], _ptr(out), cap)
+        return None if n < 0 else out[:n].copy()
+
+    def thermostat_state(self):
+        ng, nc = int(self.f64("settings")[3]), self.params.num_nh_chains
+        return {"num_temp_groups": ng, "ke2": self.f64("ke2"), "vscale": self.f64("vscale"),
+                "eta": self.f64("eta").reshape(ng, nc), "eta_dot": self.f64("etaDot").reshape(ng, nc + 1),
+                "eta_dotdot": self.f64("etaDotDot").reshape(ng, nc)}
+
+    def viscosity(self):
+        out = np.zeros(2)
+        self._ok(self.lib.momm_get_viscosity(self.h, _ptr(out)))
+        return float(out[0]), float(out[1])
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.int64)
+        self.lib.momm_counters(self.h, _ptr(out))
+        names = ("reference_kernel_launches", "force_evaluations", "constraint_calls", "velocity_constraint_calls",
+                 "reorder_calls", "step_count", "force_info_before_init", "vvb200_launches")
+        return dict(zip(names, (int(x) for x in out)))
+
+    def particles_identical(self, i, j):
+        return bool(self.lib.momm_particles_identical(self.h, int(i), int(j)))
+
+    def array_pointers(self):
+        out = (C.c_void_p * 6)()
+        self.lib.momm_array_pointers(self.h, out)
+        return dict(zip(("posq", "corr", "velm", "force", "pos_delta", "random"), (int(x or 0) for x in out)))
