@@ -15,7 +15,10 @@
 //   updateImagePositions                                          no-op (done by whichever call wrote the positions)
 // With constraints or virtual sites OpenMM's solvers must run between the sub-steps, so the split entry points are
 // used: kick -> applyVelocityConstraints | (no-op) | thermostat_delta -> applyConstraints -> finish  (440 B/particle).
-// Velocity-Verlet scheme: thermostat | vv_kick(+posDelta) -> applyConstraints -> vv_positions | vv_kick | thermostat.
+// Velocity-Verlet scheme without constraints: firstIntegrate = vvb200_step_vv_first (thermostat half step + half kick +
+// drift), secondIntegrate = vvb200_step_vv_second (half kick + thermostat half step); both scaleVelocity calls are no-ops.
+// With constraints: thermostat | vv_kick(+posDelta) -> applyConstraints -> vv_positions | vv_kick -> applyVelocityConstraints |
+// thermostat.
 #include "CudaVVKernelsB200.h"
 
 #include <iostream>
@@ -274,9 +277,15 @@ void CudaIntegrateVVStepKernel::firstIntegrate(ContextImpl &, const VVIntegrator
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);
     CudaIntegrationUtilities &integration = cu.getIntegrationUtilities();
-    VVB200_CHECK(vvb200_vv_kick(sh->plan, &b, &a, 0, 1, cu.getCurrentStream()));
-    integration.applyConstraints(integrator.getConstraintTolerance());
-    VVB200_CHECK(vvb200_vv_positions(sh->plan, &b, cu.getCurrentStream()));
+    if (!sh->constrained) {
+        // no OpenMM solver between the sub-steps: thermostat half step (the scaleVelocity call that preceded this one was
+        // deferred to here) + half kick + drift + hard wall + image mirror, fused (1 launch resident, 2 streaming)
+        VVB200_CHECK(vvb200_step_vv_first(sh->plan, &b, &a, cu.getCurrentStream()));
+    } else {
+        VVB200_CHECK(vvb200_vv_kick(sh->plan, &b, &a, 0, 1, cu.getCurrentStream()));
+        integration.applyConstraints(integrator.getConstraintTolerance());
+        VVB200_CHECK(vvb200_vv_positions(sh->plan, &b, cu.getCurrentStream()));
+    }
     integration.computeVirtualSites();
     cu.reorderAtoms();          // after the first half, like the reference (CudaVVKernels.cpp:376-381)
 }
@@ -285,8 +294,13 @@ void CudaIntegrateVVStepKernel::secondIntegrate(ContextImpl &, const VVIntegrato
     ContextSelector selector(cu);
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);
-    VVB200_CHECK(vvb200_vv_kick(sh->plan, &b, &a, 1, 0, cu.getCurrentStream()));
-    cu.getIntegrationUtilities().applyVelocityConstraints(integrator.getConstraintTolerance());
+    if (!sh->constrained) {
+        // extra forces + half kick + the thermostat half step that follows (the next scaleVelocity call is a no-op), fused
+        VVB200_CHECK(vvb200_step_vv_second(sh->plan, &b, &a, cu.getCurrentStream()));
+    } else {
+        VVB200_CHECK(vvb200_vv_kick(sh->plan, &b, &a, 1, 0, cu.getCurrentStream()));
+        cu.getIntegrationUtilities().applyVelocityConstraints(integrator.getConstraintTolerance());
+    }
     finishStep(cu, integrator.getStepSize());
 }
 
@@ -300,8 +314,8 @@ void CudaModifyDrudeNoseKernel::initialize(const System &, const VVIntegrator &,
 }
 
 void CudaModifyDrudeNoseKernel::scaleVelocity(ContextImpl &, const VVIntegrator &integrator) {
-    if (integrator.getUseMiddleScheme())
-        return;                             // fused into the passes secondIntegrate launches (see the table at the top)
+    if (integrator.getUseMiddleScheme() || !sh->constrained)
+        return;                             // fused into the calls first/secondIntegrate make (see the table at the top)
     ContextSelector selector(cu);
     vvb200_buffers b = deviceBuffers(cu);
     vvb200_step_args a = stepArgs(cu, *sh, integrator);

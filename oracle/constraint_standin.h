@@ -10,10 +10,11 @@
  * pending displacement) using posq (+posqCorrection) as the reference geometry and velm.w as the
  * inverse masses; applyVelocityConstraints rewrites velm.  This header implements that contract as
  * a fixed number of SHAKE / RATTLE sweeps over clusters of distance constraints, one cluster per
- * thread, constraints inside a cluster visited in list order -- so every consumer (the C oracle,
- * the reference-kernel harness on host and GPU, the mini-OpenMM the reference plugin and the
- * glue are linked against, and the GPU tests that call the product's split entry points) applies
- * bit-for-bit the same operator to its own buffers.  It is NOT OpenMM's solver and no physical
+ * thread, constraints inside a cluster visited in list order, every product rounded on its own
+ * (VVC_MUL: never contracted into an FMA, whatever the compiler flags of the including file) -- so
+ * every consumer (the C oracle, the reference-kernel harness on host and GPU, the mini-OpenMM the
+ * reference plugin and the glue are linked against, and the GPU tests that call the product's
+ * split entry points) applies bit-for-bit the same operator to its own buffers.  It is NOT OpenMM's solver and no physical
  * claim is made; it exists so that posDelta != oldDelta and velocities change between sub-steps.
  *
  * The includer defines, before including:
@@ -25,6 +26,28 @@
 #define VVC_CONSTRAINT_STANDIN_H_
 
 #include <stdint.h>
+
+/* a product that is never fused with a following add: nvcc contracts by default (-fmad=true), the host builds of this
+ * repository are compiled with -ffp-contract=off */
+#if defined(__CUDACC__)
+__host__ __device__ inline double vvc_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+__host__ __device__ inline float vvc_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+#define VVC_MUL(a, b) vvc_mul((a), (b))
+#else
+#define VVC_MUL(a, b) ((a) * (b))
+#endif
 
 typedef struct {
     int32_t numClusters;
@@ -59,11 +82,12 @@ VVC_FN void vvc_cluster_positions(const vvc_constraints cs, int c, const VVC_REA
             const VVC_MIXED ry = r0y + (posDelta[i].y - posDelta[j].y);
             const VVC_MIXED rz = r0z + (posDelta[i].z - posDelta[j].z);
             const VVC_MIXED d0 = (VVC_MIXED) cs.distance[k];
-            const VVC_MIXED diff = d0 * d0 - (rx * rx + ry * ry + rz * rz);
-            const VVC_MIXED rr0 = rx * r0x + ry * r0y + rz * r0z;
-            const VVC_MIXED g = diff / (2 * (wi + wj) * rr0);
-            posDelta[i].x += g * wi * r0x; posDelta[i].y += g * wi * r0y; posDelta[i].z += g * wi * r0z;
-            posDelta[j].x -= g * wj * r0x; posDelta[j].y -= g * wj * r0y; posDelta[j].z -= g * wj * r0z;
+            const VVC_MIXED diff = VVC_MUL(d0, d0) - (VVC_MUL(rx, rx) + VVC_MUL(ry, ry) + VVC_MUL(rz, rz));
+            const VVC_MIXED rr0 = VVC_MUL(rx, r0x) + VVC_MUL(ry, r0y) + VVC_MUL(rz, r0z);
+            const VVC_MIXED g = diff / VVC_MUL(VVC_MUL((VVC_MIXED) 2, wi + wj), rr0);
+            const VVC_MIXED gi = VVC_MUL(g, wi), gj = VVC_MUL(g, wj);
+            posDelta[i].x += VVC_MUL(gi, r0x); posDelta[i].y += VVC_MUL(gi, r0y); posDelta[i].z += VVC_MUL(gi, r0z);
+            posDelta[j].x -= VVC_MUL(gj, r0x); posDelta[j].y -= VVC_MUL(gj, r0y); posDelta[j].z -= VVC_MUL(gj, r0z);
         }
 }
 
@@ -81,9 +105,12 @@ VVC_FN void vvc_cluster_velocities(const vvc_constraints cs, int c, const VVC_RE
             vvc_load_pos(posq, corr, j, xj);
             const VVC_MIXED r0x = xi[0] - xj[0], r0y = xi[1] - xj[1], r0z = xi[2] - xj[2];
             const VVC_MIXED vx = velm[i].x - velm[j].x, vy = velm[i].y - velm[j].y, vz = velm[i].z - velm[j].z;
-            const VVC_MIXED k2 = (vx * r0x + vy * r0y + vz * r0z) / ((wi + wj) * (r0x * r0x + r0y * r0y + r0z * r0z));
-            velm[i].x -= k2 * wi * r0x; velm[i].y -= k2 * wi * r0y; velm[i].z -= k2 * wi * r0z;
-            velm[j].x += k2 * wj * r0x; velm[j].y += k2 * wj * r0y; velm[j].z += k2 * wj * r0z;
+            const VVC_MIXED vr = VVC_MUL(vx, r0x) + VVC_MUL(vy, r0y) + VVC_MUL(vz, r0z);
+            const VVC_MIXED r2 = VVC_MUL(r0x, r0x) + VVC_MUL(r0y, r0y) + VVC_MUL(r0z, r0z);
+            const VVC_MIXED k2 = vr / VVC_MUL(wi + wj, r2);
+            const VVC_MIXED ki = VVC_MUL(k2, wi), kj = VVC_MUL(k2, wj);
+            velm[i].x -= VVC_MUL(ki, r0x); velm[i].y -= VVC_MUL(ki, r0y); velm[i].z -= VVC_MUL(ki, r0z);
+            velm[j].x += VVC_MUL(kj, r0x); velm[j].y += VVC_MUL(kj, r0y); velm[j].z += VVC_MUL(kj, r0z);
         }
 }
 
