@@ -300,9 +300,11 @@ int vvb200_measure_temperatures(vvb200_plan *plan, const vvb200_buffers *buf, co
 int vvb200_set_resident_mode(vvb200_plan *plan, int mode);
 int64_t vvb200_resident_launch_count(const vvb200_plan *plan);
 
-/* Optional per-kernel timing of the middle step for bench.py's roofline: CUDA events are recorded on
- * the launching stream around pass A (kick + reductions) and pass B (scale + drift + position write) for
- * up to max_steps steps (0 disables).  vvb200_profile_read synchronises on the last event, returns the
+/* Optional per-kernel timing for bench.py's roofline: CUDA events are recorded on the launching stream
+ * around the pass-A kernel (kick and / or reductions) and the pass-B kernel (scale / drift / position
+ * write) of every step-like call -- vvb200_step_middle, vvb200_step_vv_first / _second, and the split
+ * calls vvb200_middle_kick, vvb200_thermostat, vvb200_middle_thermostat_delta, vvb200_middle_finish --
+ * for up to max_steps such calls (0 disables).  vvb200_profile_read synchronises on the last event, returns the
  * summed durations in milliseconds and the number of steps they cover, and restarts the sampling. */
 int vvb200_profile_enable(vvb200_plan *plan, int max_steps);
 int vvb200_profile_read(vvb200_plan *plan, double *ms_pass_a, double *ms_pass_b, int32_t *steps);

@@ -65,6 +65,18 @@ template <int MODE, class T> __device__ __forceinline__ T vv_sqrt(T x) {
 }
 __device__ __forceinline__ float vv_recip(float x) { return 1.0f / x; }
 __device__ __forceinline__ double vv_recip(double x) { return 1.0 / x; }
+// Reciprocal for the MASSES that enter the kinetic-energy / centre-of-mass reductions (m = 1/velm.w, mu = m1 m2/(m1+m2)):
+// hardware seed (upper 20 mantissa bits) + two Newton steps, 5 instructions instead of the ~14 of the IEEE division
+// routine, within 1 ulp of it.  The reductions are the only consumers: the sums change at the 1e-16 level, nothing that
+// is written back per particle goes through here.
+__device__ __forceinline__ double rcpMass(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ float rcpMass(float x) { return 1.0f / x; }
 
 // ---- streaming loads / stores ------------------------------------------------------------------
 __device__ __forceinline__ D4 ld_stream(const D4 *p) {
@@ -1116,6 +1128,21 @@ static cudaError_t launchA(KParams k, int numSM, cudaStream_t st) {
     return launchStreaming(kick_reduce_kernel<MODE, KICK, EXTRA>, grid, BTHREADS, cfg.smem, st, k);
 }
 
+// the reduce-only pass without the cosine perturbation: its own latency-organised kernel (vvb200_stream.cuh)
+template <int MODE>
+static cudaError_t launchRed(KParams k, int numSM, cudaStream_t st) {
+    static CfgCache cache;
+    const int slot = currentDeviceSlot();
+    if (!cache.valid[slot]) {
+        cache.cfg[slot] = configure(reduce_kernel<MODE>, smemBytesRed<MODE>, "VVB200_STAGES_R", "VVB200_BLOCKS_R", MINBLOCKS_RED, BTHREADS, 3);
+        cache.valid[slot] = true;
+    }
+    const LaunchCfg &cfg = cache.cfg[slot];
+    k.stagesA = cfg.stages;
+    const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
+    return launchStreaming(reduce_kernel<MODE>, grid, BTHREADS, cfg.smem, st, k);
+}
+
 template <int MODE, int VARIANT, bool EXTRA>
 static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
     // the scale-only variant stages 36 B/particle instead of 68: it needs a deeper ring for the same bytes in flight
@@ -1139,6 +1166,14 @@ static bool needsExtra(const KParams &k) { return k.cosine || k.hasField || k.ha
 
 template <int KICK>
 static cudaError_t dispatchA(int precision, bool, const KParams &k, int numSM, cudaStream_t st) {
+    static const int dedicatedReduce = envInt("VVB200_REDUCE_KERNEL", 1);
+    if (KICK == KICK_NONE && !k.cosine && !k.kickOnly && dedicatedReduce) {
+        switch (precision) {
+        case VVB200_SINGLE: return launchRed<VVB200_SINGLE>(k, numSM, st);
+        case VVB200_MIXED: return launchRed<VVB200_MIXED>(k, numSM, st);
+        default: return launchRed<VVB200_DOUBLE>(k, numSM, st);
+        }
+    }
     switch (precision * 2 + (needsExtra(k) ? 1 : 0)) {
     case 0: return launchA<VVB200_SINGLE, KICK, false>(k, numSM, st);
     case 1: return launchA<VVB200_SINGLE, KICK, true>(k, numSM, st);
@@ -1669,12 +1704,16 @@ extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, con
     if ((rc = tryResident<KICK_NONE, VAR_VV_FIRST>(p, k, hasNH(p), st, &resident))) return rc;
     if (resident)
         return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
+    profMark(p->dev, 0, st);
     if (hasNH(p)) {
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
     }
+    profMark(p->dev, 1, st);
+    profMark(p->dev, 2, st);
     CUDA_TRY((dispatchB<VAR_VV_FIRST>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 3, st);
     return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
 }
 
@@ -1697,12 +1736,16 @@ extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, co
         if (resident)
             return VVB200_OK;
     }
+    profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_VV>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 1, st);
+    profMark(p->dev, 2, st);
     if (hasNH(p)) {
         CUDA_TRY((dispatchB<VAR_SCALE_ONLY>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
     }
+    profMark(p->dev, 3, st);
     return VVB200_OK;
 }
 
@@ -1717,8 +1760,12 @@ extern "C" int vvb200_middle_kick(vvb200_plan *p, const vvb200_buffers *b, const
     KParams k = makeParams(p, b, a);
     k.fuseNHC = 0;
     k.kickOnly = 1;
+    profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_MIDDLE>(p->precision, k.cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 1, st);
+    profMark(p->dev, 2, st);
+    profMark(p->dev, 3, st);
     return VVB200_OK;
 }
 
@@ -1736,10 +1783,14 @@ extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const 
     if ((rc = tryResident<KICK_NONE, VAR_SCALE_ONLY>(p, k, true, st, &resident))) return rc;
     if (resident)
         return VVB200_OK;
+    profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 1, st);
+    profMark(p->dev, 2, st);
     CUDA_TRY((dispatchB<VAR_SCALE_ONLY>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 3, st);
     return VVB200_OK;
 }
 
@@ -1776,16 +1827,24 @@ extern "C" int vvb200_middle_thermostat_delta(vvb200_plan *p, const vvb200_buffe
     KParams k = makeParams(p, b, a);
     k.posDelta = b->pos_delta;
     k.oldDelta = p->dev->oldDelta;
+    profMark(p->dev, 0, st);
     if (hasNH(p)) {
         bool resident = false;
         if ((rc = tryResident<KICK_NONE, VAR_SCALE_DELTA>(p, k, true, st, &resident))) return rc;
-        if (resident)
+        if (resident) {
+            profMark(p->dev, 1, st);
+            profMark(p->dev, 2, st);
+            profMark(p->dev, 3, st);
             return VVB200_OK;
+        }
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
     }
+    profMark(p->dev, 1, st);
+    profMark(p->dev, 2, st);
     CUDA_TRY((dispatchB<VAR_SCALE_DELTA>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
+    profMark(p->dev, 3, st);
     return VVB200_OK;
 }
 
@@ -1829,8 +1888,12 @@ extern "C" int vvb200_middle_finish(vvb200_plan *p, const vvb200_buffers *b, voi
         KParams k = makeParams(p, b, nullptr);
         k.posDelta = b->pos_delta;
         k.oldDelta = d->oldDelta;
+        profMark(d, 0, st);
+        profMark(d, 1, st);
+        profMark(d, 2, st);
         CUDA_TRY((dispatchB<VAR_FINISH>(p->precision, false, k, d->numSM, st)));
         p->launches++;
+        profMark(d, 3, st);
         return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);
     }
     const int grid = elementwiseGrid(p, p->N);

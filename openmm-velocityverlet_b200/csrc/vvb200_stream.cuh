@@ -303,7 +303,7 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
                 // after the block barrier (passAPhase23): a Langevin pair partner may still need the pre-kick value
                 if constexpr (!RESIDENT) st_stream(velm + idx, v);
             }
-            const mixed mass = v.w != 0 ? vv_recip(v.w) : (mixed) 0;
+            const mixed mass = v.w != 0 ? rcpMass(v.w) : (mixed) 0;
             vel[it] = v;
             vel[it].w = mass;
             pub.vx[loc] = v.x; pub.vy[loc] = v.y; pub.vz[loc] = v.z; pub.m[loc] = mass;
@@ -312,12 +312,14 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
                 if (cosine && v.w != 0)   // cosineAccelerate.cu:26
                     acc[3] += mass * v.x * 2 * cph;
             }
-            // Atom-group energy of a normal particle (drudeNoseHoover.cu:76-83).  The reference sums m|v - V_mol|^2;
-            // here sum m|v|^2 is taken per particle and M|V_mol|^2 subtracted once per molecule in phase 2 (the
-            // same number up to fp64 reassociation: every massive member of a thermostat molecule is in the sum),
-            // so no particle has to wait for its molecule's V.
-            if (!p.kickOnly && (meta[it] & VVB200_META_NH) && v.w != 0 &&
-                ((meta[it] >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_NONE) {
+            // Atom-group energy (drudeNoseHoover.cu:76-114).  The reference sums m|v - V_mol|^2 over the normal particles
+            // and (m1+m2)|v_cm - V_mol|^2 over the Drude pairs; here EVERY massive thermostat particle adds m|v|^2, then
+            //   - M|V_mol|^2 leaves once per molecule in phase 2 (every massive member of a thermostat molecule is in the
+            //     sum), so no particle has to wait for its molecule's V, and
+            //   - mu|v1 - v2|^2 leaves once per Drude pair in phase 3 and goes to the Drude group, because
+            //     m1|v1|^2 + m2|v2|^2 = (m1+m2)|v_cm|^2 + mu|v1-v2|^2: the pair phase needs no pair-COM velocity at all.
+            // Same numbers up to fp64 reassociation (<= 1e-15 per term; the tests hold the sums to 1e-12).
+            if (!p.kickOnly && (meta[it] & VVB200_META_NH) && v.w != 0) {
                 acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
                 if (cosine) {
                     acc[4] += v.x * cph * mass;
@@ -422,8 +424,8 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
         }
     }
 
-    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: pair-COM term of
-    //      the atom group (in absolute velocities, see phase 1) and the relative-motion (Drude) group ----------
+    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: the relative-motion energy
+    //      mu|v1 - v2|^2 is the Drude group's, and leaves the atom group (see phase 1) -------------------------------
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
         const uint32_t mw = meta[it];
@@ -433,22 +435,16 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
         const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
         const mixed4 v = vel[it];     // .w = mass
         const mixed mass1 = v.w, mass2 = pub.m[ploc];
-        const mixed v2x = pub.vx[ploc], v2y = pub.vy[ploc], v2z = pub.vz[ploc];
-        const mixed totalMass = mass1 + mass2;
-        const mixed invTotalMass = vv_recip(totalMass);
-        const mixed m1f = invTotalMass * mass1, m2f = invTotalMass * mass2;
-        const mixed redMass = mass1 * m2f;       // = 1 / ((m1+m2) w1 w2)
-        const mixed cmx = v.x * m1f + v2x * m2f, cmy = v.y * m1f + v2y * m2f, cmz = v.z * m1f + v2z * m2f;
-        const mixed rx = v.x - v2x, ry = v.y - v2y, rz = v.z - v2z;
-        acc[0] += (cmx * cmx + cmy * cmy + cmz * cmz) * totalMass;
-        acc[2] += (rx * rx + ry * ry + rz * rz) * redMass;
+        const mixed redMass = mass1 * mass2 * rcpMass(mass1 + mass2);       // = 1 / ((m1+m2) w1 w2)
+        const mixed rx = v.x - pub.vx[ploc], ry = v.y - pub.vy[ploc], rz = v.z - pub.vz[ploc];
+        const mixed e = (rx * rx + ry * ry + rz * rz) * redMass;
+        acc[2] += e;
+        acc[0] -= e;
         if (cosine) {
-            const mixed c1 = pub.cph[loc], c2 = pub.cph[ploc];
-            const mixed cmd = c1 * m1f + c2 * m2f, rd = c1 - c2;
-            acc[4] += cmx * cmd * totalMass;
-            acc[7] += cmd * cmd * totalMass;
-            acc[6] += rx * rd * redMass;
-            acc[9] += rd * rd * redMass;
+            const mixed rd = pub.cph[loc] - pub.cph[ploc];
+            const mixed b = rx * rd * redMass, c = rd * rd * redMass;
+            acc[6] += b; acc[4] -= b;
+            acc[9] += c; acc[7] -= c;
         }
     }
 }
@@ -697,6 +693,199 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
         nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
     } else {
         lastBlockFinish<MODE, NR>(p, sm, cosine, tid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce-only pass: molecular COM + group kinetic energies of the CURRENT velocities (+ NH chains)
+// ------------------------------------------------------------------------------------------------
+// What the thermostat needs when the kick is not part of the same call: the constraint-bearing flow (OpenMM's velocity
+// constraints run between the kick and the thermostat, CudaVVKernels.cpp:151), the velocity-Verlet scheme's leading half
+// step, vvb200_thermostat, vvb200_measure_temperatures.  36 B/particle (velm + slot word), nothing to write but comV.
+// kick_reduce_kernel<KICK_NONE> ran it at 0.39 of the copy roofline, and ncu says why (profiles/ncu_r02_reduce_summary.txt):
+// the SHARED-MEMORY pipe is saturated (l1tex lsu wavefronts 82 % of peak, 40 % of them bank conflicts), then the issue
+// slots (a conflict-free variant with per-lane selects ran 175M warp instructions at 66 % issue utilisation) -- not DRAM
+// (38 %), not fp64 (31 %); a deeper ring or a fourth block changes nothing.  This kernel does the same arithmetic, in the
+// same per-thread order (so its sums are bit-identical to pass A's), with fewer shared-memory wavefronts AND fewer
+// instructions per particle:
+//   - nothing is re-published: the molecule phase reads (vx, vy, vz, w) straight from the TMA stage and recomputes the
+//     mass (rcpMass: 5 instructions);
+//   - the pair phase needs only mu|v1 - v2|^2 (see passAPhase1): the Drude's lane reads its partner from the stage;
+//   - with nothing written to shared memory there is NO block barrier: every warp goes from the stage's `full` barrier to
+//     its `empty` arrival on its own.
+// Cosine runs (which also need cos(kz) per particle, published once) keep the general kernel.
+template <int MODE> struct StageRed {
+    typename Prec<MODE>::mixed4 velm[PADT];
+    uint32_t meta[PADT];
+    int32_t molInfo[MAXMOL + 8];
+    int32_t desc[8];
+};
+struct ScratchRed {
+    double red[CTHREADS / 32][VVB200_NRED];
+    unsigned long long peerSeq;
+    unsigned int ticket;
+};
+template <int MODE> constexpr size_t smemBytesRed(int stages) {
+    return roundUp128(sizeof(StageRed<MODE>)) * stages + roundUp128(sizeof(ScratchRed)) + 16 * stages + 128;
+}
+#ifndef MINBLOCKS_RED
+#define MINBLOCKS_RED 3
+#endif
+
+template <int MODE>
+__global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const KParams p) {
+    typedef Prec<MODE> P;
+    typedef typename P::mixed mixed;
+    typedef typename P::mixed4 mixed4;
+    typedef StageRed<MODE> Stage;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ NhcDevice nhcS;
+    const int stages = p.stagesA;
+    constexpr size_t stageBytes = roundUp128(sizeof(Stage));
+    ScratchRed &sm = *reinterpret_cast<ScratchRed *>(smemRaw + stageBytes * stages);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smemRaw + stageBytes * stages + roundUp128(sizeof(ScratchRed)));
+    uint64_t *empty = full + stages;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbarInit(full + s, 1);
+            mbarInit(empty + s, CTHREADS);
+        }
+        fenceBarrierInit();
+    }
+    __syncthreads();
+    gridDepWait();
+    const bool useCOM = p.useCOM;
+
+    if (tid >= CTHREADS) {
+        // ===== producer warp =====
+        if (tid != CTHREADS)
+            return;
+        int s = 0;
+        uint32_t phase = 0;
+        for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
+            const int4 d0 = __ldg(p.tileDesc + 2 * tile), d1 = __ldg(p.tileDesc + 2 * tile + 1);
+            mbarWait(empty + s, phase ^ 1);
+            Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+            const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
+            const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
+            st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
+            mbarArriveExpectTx(full + s, cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u);
+            bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
+            bulkLoad(st.meta, p.slotMeta + a0, cnt * 4u, full + s);
+            if (mcnt) bulkLoad(st.molInfo, p.tileMolInfo + ma0, mcnt * 4u, full + s);
+            if (++s == stages) { s = 0; phase ^= 1; }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    if (p.fuseNHC)
+        nhcFetch(&nhcS, p.nhc, tid, 0);
+    mixed acc[3] = {0, 0, 0};
+    mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
+        mbarWait(full + s, phase);
+        Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+        const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
+        const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
+        const mixed4 *sv = st.velm + sl0;      // (vx, vy, vz, 1/m) per tile-local slot
+        // ---- per particle: m|v|^2 of every massive thermostat particle (see passAPhase1) and, on the Drude's lane, the
+        //      pair's relative-motion energy mu|v1 - v2|^2 (drudeNoseHoover.cu:99-114) ----
+        mixed pairRel[ITEMS];
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const int loc = it * CTHREADS + tid;
+            pairRel[it] = 0;
+            if (t0 + loc < t1) {
+                const mixed4 v = sv[loc];
+                const uint32_t mw = st.meta[sl0 + loc];
+                const mixed mass = v.w != 0 ? rcpMass(v.w) : (mixed) 0;
+                if ((mw & VVB200_META_NH) && v.w != 0)
+                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
+                if ((mw & VVB200_META_NH) && ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_DRUDE) {
+                    const mixed4 q = sv[loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS];
+                    const mixed mass2 = rcpMass(q.w);
+                    const mixed redMass = mass * mass2 * rcpMass(mass + mass2);
+                    const mixed rx = v.x - q.x, ry = v.y - q.y, rz = v.z - q.z;
+                    pairRel[it] = (rx * rx + ry * ry + rz * rz) * redMass;
+                }
+            }
+        }
+        // ---- molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), COM_LANES lanes per molecule ----
+        if (nMol > 0) {
+            const int grp = tid / COM_LANES, sub = tid % COM_LANES;
+            for (int jb = 0; jb < nMol; jb += CTHREADS / COM_LANES) {
+                const int j = jb + grp;
+                const bool active = j < nMol;
+                mixed sx = 0, sy = 0, sz = 0, comMass = 0;
+                uint32_t info = 0;
+                int mol = 0;
+                if (active) {
+                    info = (uint32_t) st.molInfo[ml0 + j];
+                    mol = molFirst >= 0 ? molFirst + j : p.tileMolList[m0 + j];
+                    if (!MOLINFO_SCATTERED(info)) {
+                        const int first = MOLINFO_FIRST(info), cnt = MOLINFO_COUNT(info);
+                        for (int k = first + sub; k < first + cnt; k += COM_LANES) {
+                            const mixed4 q = sv[k];
+                            const mixed mass = q.w != 0 ? rcpMass(q.w) : (mixed) 0;
+                            sx += q.x * mass; sy += q.y * mass; sz += q.z * mass;
+                            comMass += mass;
+                        }
+                    } else if (sub == 0) {
+                        const int cnt = p.particlesInMolecules[2 * mol], start = p.particlesInMolecules[2 * mol + 1];
+                        for (int k = 0; k < cnt; k++) {
+                            const int loc = p.sortedByMol[start + k] - t0;
+                            if (loc < 0 || loc >= t1 - t0) continue;
+                            const mixed4 q = sv[loc];
+                            const mixed mass = q.w != 0 ? rcpMass(q.w) : (mixed) 0;
+                            sx += q.x * mass; sy += q.y * mass; sz += q.z * mass;
+                            comMass += mass;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = COM_LANES / 2; off > 0; off >>= 1) {
+                    sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                    sy += __shfl_xor_sync(0xffffffffu, sy, off);
+                    sz += __shfl_xor_sync(0xffffffffu, sz, off);
+                    comMass += __shfl_xor_sync(0xffffffffu, comMass, off);
+                }
+                if (active && sub == 0 && MOLINFO_FRAGMENT(info)) {
+                    double *fp = p.fragPartials + 5 * (size_t) p.tileMolFrag[m0 + j];
+                    fp[0] = (double) sx; fp[1] = (double) sy; fp[2] = (double) sz; fp[3] = (double) comMass; fp[4] = 0.0;
+                } else if (active && sub == 0) {
+                    mixed4 V;
+                    V.w = vv_recip(comMass);
+                    V.x = sx * V.w; V.y = sy * V.w; V.z = sz * V.w;
+                    st_stream(comV + mol, V);
+                    const mixed mv2 = (V.x * V.x + V.y * V.y + V.z * V.z) * comMass;
+                    acc[1] += mv2;
+                    acc[0] -= mv2;
+                }
+            }
+        }
+        mbarArrive(empty + s);      // this thread is done reading the stage
+        if (++s == stages) { s = 0; phase ^= 1; }
+        // the pair terms join the sums AFTER the molecule terms: the order pass A adds them in (bit-identical sums)
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            acc[2] += pairRel[it];
+            acc[0] -= pairRel[it];
+        }
+    }
+
+    if (tid == 0) gridDepLaunch();
+    if (!blockReduceAndTicket<3>(p, sm, acc, tid))
+        return;
+    if (p.fuseNHC) {
+        lastBlockFinish<MODE, 3>(p, sm, false, tid, &nhcS);
+        consumerBarrier();
+        nhcStore(p.nhc, &nhcS, tid);
+    } else {
+        lastBlockFinish<MODE, 3>(p, sm, false, tid);
     }
 }
 
