@@ -137,9 +137,13 @@ template <int MODE, bool EXTRA, bool FORCE> constexpr size_t smemBytesA(int stag
 #endif
 __host__ __device__ constexpr int passABlocks(int kick) { return kick == KICK_NONE ? MINBLOCKS_A_REDUCE : MINBLOCKS_A; }
 
-// lanes that cooperate on one molecule's centre of mass
+// Lanes that cooperate on one molecule's centre of mass.  The butterfly that adds their partial sums up costs
+// log2(COM_LANES) x 8 shuffles per group, and shuffles share the shared-memory (LSU) pipe that bounds these kernels:
+// 4 lanes instead of 8 took the reduce-only pass from 176 to 149 us for 16.4M particles and left pass A where it was
+// (242 us).  The same value everywhere: the group partition decides which thread adds a molecule's M|V|^2, and the
+// kernels' sums are meant to be bit-identical.
 #ifndef COM_LANES
-#define COM_LANES 8
+#define COM_LANES 4
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -729,7 +733,7 @@ template <int MODE> constexpr size_t smemBytesRed(int stages) {
     return roundUp128(sizeof(StageRed<MODE>)) * stages + roundUp128(sizeof(ScratchRed)) + 16 * stages + 128;
 }
 #ifndef MINBLOCKS_RED
-#define MINBLOCKS_RED 3
+#define MINBLOCKS_RED 4       // 56 registers: warps are independent here (no block barrier), a fourth block is worth 3 %
 #endif
 
 template <int MODE>
