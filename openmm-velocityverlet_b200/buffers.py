@@ -25,6 +25,17 @@ class DeviceBuffers:
         self.random = t(host.random)
         self.pos_delta = torch.zeros_like(self.velm) if with_pos_delta else None
 
+    @classmethod
+    def from_tensors(cls, precision, posq, corr, velm, force, random=None, box=(1.0, 1.0, 1.0), pos_delta=None):
+        """wrap CUDA tensors that already hold OpenMM's layouts (e.g. a state generated on the device)"""
+        import torch
+        self = cls.__new__(cls)
+        self.precision, self.box = precision, box
+        self.posq, self.corr, self.velm, self.force = posq, corr, velm, force
+        self.random = random if random is not None else torch.zeros((1, 4), dtype=torch.float32, device=velm.device)
+        self.pos_delta = pos_delta
+        return self
+
     def c_struct(self):
         p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None
         return _Buffers(p(self.posq), p(self.corr), p(self.velm), p(self.force), p(self.pos_delta), p(self.random))

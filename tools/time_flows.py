@@ -60,10 +60,16 @@ def main():
                 torch.cuda.synchronize()
                 a, b, k = plan.profile_read()
                 plan.profile_enable(0)
-                done[fn] = (1e3 * a / max(k, 1), 1e3 * b / max(k, 1), 1e3 * e0.elapsed_time(e1) / reps)
+                # the same call again WITHOUT the per-kernel events (an event between two launches forbids their PDL overlap)
+                e0.record()
+                for _ in range(5 * reps):
+                    call(bufs)
+                e1.record()
+                torch.cuda.synchronize()
+                done[fn] = (1e3 * a / max(k, 1), 1e3 * b / max(k, 1), 1e3 * e0.elapsed_time(e1) / (5 * reps))
             us = done[fn][which]
             gbs = bpp * spec.n / (us * 1e-6) / 1e9 if us > 0 else 0
-            print(f"  {label:36s} {us:8.1f} us  {gbs:7.0f} GB/s  {gbs / PEAK:5.3f} of measured peak   (call total {done[fn][2]:.1f} us)", flush=True)
+            print(f"  {label:36s} {us:8.1f} us  {gbs:7.0f} GB/s  {gbs / PEAK:5.3f} of measured peak   (whole call, no events: {done[fn][2]:.1f} us)", flush=True)
         del plan, bufs
 
 
