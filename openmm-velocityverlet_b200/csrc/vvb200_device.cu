@@ -146,10 +146,28 @@ struct PeerCtx {
     volatile unsigned int *timedOut;     // mapped host memory: set when a wait expired
 };
 
+// One 16-byte record per scale factor: the value and a tag, written with ONE 128-bit store and read with one 128-bit load
+// (a 16-byte aligned access is a single transaction), so a reader that sees the tag has the value -- no fence between
+// payload and flag, nothing to fetch after the flag.
+struct __align__(16) FactorRec {
+    double value;
+    unsigned long long tag;
+};
+__device__ __forceinline__ void factorPublish(FactorRec *r, double value, unsigned long long tag) {
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(r), "l"(__double_as_longlong(value)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ bool factorPoll(const FactorRec *r, unsigned long long tag, double *value) {
+    unsigned long long v, t;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(r) : "memory");
+    *value = __longlong_as_double((long long) v);
+    return t == tag;
+}
+
 struct KParams {
     int N, paddedN, numTiles;
     const int4 *tileDesc;                      // 2 x int4 per tile, see vvb200_stream.cuh
     const int32_t *tileMolList, *tileMolInfo;
+    const uint32_t *tilePairs;                 // per tile: its thermostatted Drude pairs, (Drude slot) | (parent slot) << 16, tile-local
     const uint32_t *slotMeta;
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
@@ -188,6 +206,14 @@ struct KParams {
     int tileBegin, tileEnd, accumulateRed;
     int pdl;     // launch with programmatic stream serialization (host side only)
     unsigned int *gridGen;   // generation word of its grid barrier
+    // pass B synchronised with pass A's last block through a device word instead of waiting for the whole grid (see
+    // "early hand-over" in vvb200_stream.cuh): 0 = reset by pass A, 1 = every tile's velocities are stored and visible,
+    // 2 = this step's scale factors are in nhc->vscale
+    unsigned int *syncFlag;
+    unsigned int *tileTicket;      // pass B under the hand-over takes its tiles from this counter (zeroed by pass A's block 0)
+    FactorRec *factorRec;          // [4]: this step's three scale factors and the velocity bias, each with its own "valid" tag
+    int flagSync;
+    int tileReverse;               // ... starting from the last tile
     // multi-GPU: pass A's last block exchanges the reduction vector with the peers before it advances the chains
     int peerOn;
     PeerCtx peer;
@@ -306,6 +332,117 @@ __device__ void nhcFinish(NhcDevice *s, double dt, int g, const double *red = nu
     s->vscale[g] = scale;
     if (g == 0)
         s->vBias = V;
+}
+
+// ---- the chain update cut where the scale factor is known ---------------------------------------------------------
+// propagateNHChain (VVIntegrator.cpp:340-376) with loopsPerStep == 1 (the constructor's default) touches this step's
+// kinetic energy in exactly one place before the factor is final: etaDotDot[0].  Everything above it in the first sweep
+// (the chains ich = nc-1 .. 1 and the exponential that multiplies etaDot[0]) depends on the previous step only, and
+// everything after `factor` only prepares the next step.  So the block that finishes the reduction runs
+//     nhcPre   at kernel start, while the first tiles are still in flight (every block: any of them may arrive last)
+//     nhcCrit  ke2 -> etaDotDot[0] -> etaDot[0] -> factor = exp(-dt/2 etaDot[0]): one division and ONE exp on the
+//              critical path instead of six dependent exps and four divisions; the factor is published right away
+//     nhcPost  eta, the second sweep, the state for the next step -- off the critical path
+// The operations, their operands and their order are those of nhcPropagateT (bit-identical results); other loop counts
+// and groups without a thermostat mass keep the unsplit routine inside nhcCrit.
+__device__ __forceinline__ bool nhcSplittable(const NhcDevice *s, int g) {
+    return s->loops == 1 && g < s->numTG && s->etaMass[g][0] > 0;
+}
+
+__device__ __noinline__ double nhcPre(NhcDevice *s, int g, double dt) {
+    if (!nhcSplittable(s, g))
+        return 0.0;
+    const int nc = s->nc;
+    const double h2 = dt / s->loops / 2, h4 = h2 / 2, h8 = h4 / 2;
+    for (int k = nc - 1; k >= 1; k--) {
+        const double e = exp(-h8 * s->etaDot[g][k + 1]);
+        double x = s->etaDot[g][k];
+        x *= e;
+        x += s->etaDotDot[g][k] * h4;
+        x *= e;
+        s->etaDot[g][k] = x;
+    }
+    return exp(-h8 * s->etaDot[g][1]);
+}
+
+// threads 0..2 of the block that holds the final sums; returns nothing: ke2 / vscale / vBias land in *s
+template <bool COS>
+__device__ __noinline__ void nhcCrit(NhcDevice *s, double dt, int g, const double *red, double e0) {
+    double V = 0.0;
+    if (COS)
+        V = red[3] * s->invMassTotal;
+    double ke2 = red[g];
+    if (COS)
+        ke2 = red[g] - 2.0 * V * red[4 + g] + V * V * red[7 + g];
+    double scale = 1.0;
+    if (g < s->numTG) {
+        if (nhcSplittable(s, g)) {
+            const double h2 = dt / s->loops / 2, h4 = h2 / 2;
+            const double dd = (ke2 - s->NkbT[g]) / s->etaMass[g][0];
+            double x = s->etaDot[g][0];
+            x *= e0;
+            x += dd * h4;
+            x *= e0;
+            s->etaDot[g][0] = x;
+            s->etaDotDot[g][0] = dd;
+            scale = exp(-h2 * x);       // factor = 1.0 * exp(...): the product with 1.0 is exact
+        } else if (s->etaMass[g][0] > 0) {
+            scale = nhcPropagate(s, g, dt, ke2);
+        }
+    } else {
+        ke2 = 0.0;
+    }
+    s->ke2[g] = ke2;
+    s->vscale[g] = scale;
+    if (g == 0)
+        s->vBias = V;
+}
+
+__device__ __noinline__ void nhcPost(NhcDevice *s, double dt, int g, double e0) {
+    if (!nhcSplittable(s, g))
+        return;
+    const int nc = s->nc;
+    const double h2 = dt / s->loops / 2, h4 = h2 / 2, h8 = h4 / 2;
+    const double kT = BOLTZ_D * s->tTarget[g];
+    const double ke2 = s->ke2[g], factor = s->vscale[g];
+    for (int k = 0; k < nc; k++)
+        s->eta[g][k] += h2 * s->etaDot[g][k];
+    const double dd = (ke2 * factor * factor - s->NkbT[g]) / s->etaMass[g][0];
+    s->etaDotDot[g][0] = dd;
+    double x = s->etaDot[g][0];
+    x *= e0;
+    x += dd * h4;
+    x *= e0;
+    s->etaDot[g][0] = x;
+    for (int k = 1; k < nc; k++) {
+        const double e = exp(-h8 * s->etaDot[g][k + 1]);
+        double y = s->etaDot[g][k];
+        y *= e;
+        const double ddk = (s->etaMass[g][k - 1] * s->etaDot[g][k - 1] * s->etaDot[g][k - 1] - kT) / s->etaMass[g][k];
+        s->etaDotDot[g][k] = ddk;
+        y += ddk * h4;
+        y *= e;
+        s->etaDot[g][k] = y;
+    }
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded wait for *f >= want (a producer that never comes must not hang the device): false when it expired (~2 s)
+__device__ __forceinline__ bool waitFlagAtLeast(const unsigned int *f, unsigned int want) {
+    const long long c0 = clock64();
+    while (ld_acquire_gpu(f) < want) {
+        if (clock64() - c0 > 4000000000LL)
+            return false;
+        __nanosleep(40);
+    }
+    return true;
 }
 
 template <bool COS>
@@ -731,6 +868,7 @@ struct vvb200_device_state {
     int numTiles = 0;
     int4 *tileDesc = nullptr;
     int32_t *tileMolList = nullptr, *tileMolInfo = nullptr;
+    uint32_t *tilePairs = nullptr;
     int stagesA = 0, stagesB = 0, blocksPerSM = 0;   // 0: chosen per kernel from the shared-memory budget
     uint32_t *slotMeta = nullptr;
     int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
@@ -752,9 +890,11 @@ struct vvb200_device_state {
     void *comV = nullptr, *comCbar = nullptr, *ldForce = nullptr;
     double *partials = nullptr;
     NhcDevice *nhc = nullptr;
-    unsigned int *counter = nullptr;   // [0] arrival counter of the last-block reductions, [1] grid-barrier generation
+    unsigned int *counter = nullptr;   // [0] arrival counter of the last-block reductions, [32] grid-barrier generation, [64] pass A -> pass B hand-over word, [96] pass B's tile ticket, [128..143] the four factor records
     int64_t residentLaunches = 0;
     int pdl = 1;                       // VVB200_PDL at upload time
+    int handOver = 1;                  // VVB200_HANDOVER at upload time: pass B takes over from pass A through the hand-over word
+    int tileReverse = 1;               // VVB200_B_REVERSE at upload time
     int residentMode = -1;
     int residentMaxParticles = -1;     // -1: from the environment (VVB200_RESIDENT_MAX_PARTICLES, default 120000)             // -1: from the environment (VVB200_RESIDENT, default on), 0 off, 1 on
     bool extraForcesValid = false;   // VV scheme: forceExtra is zero until the first second half
@@ -859,6 +999,8 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     }
     d->numTiles = (int) p->tileStart.size() - 1;
     d->pdl = envInt("VVB200_PDL", 1) ? 1 : 0;
+    d->handOver = envInt("VVB200_HANDOVER", 1) ? 1 : 0;
+    d->tileReverse = envInt("VVB200_B_REVERSE", 1) ? 1 : 0;
 
     // per tile-local molecule: first slot, count, contiguity
     std::vector<int32_t> molInfo(p->tileMolList.size(), 0);
@@ -885,8 +1027,12 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
             }
         }
     }
-    // tile descriptors: (t0, t1, m0, nMol), (molFirst or -1, 0, 0, 0)
+    // tile descriptors: (t0, t1, m0, nMol), (molFirst or -1, pair offset, pair count, 0)
+    // The thermostatted Drude pairs of a tile as a dense list, so that the pair phase of the reductions runs on
+    // consecutive lanes (one pair per thread) instead of on the one lane in three that happens to hold a Drude particle:
+    // tile-local slots (Drude | parent << 16), each tile's list padded to a multiple of 4 entries for the bulk copies.
     std::vector<int32_t> desc((size_t) d->numTiles * 8, 0);
+    std::vector<uint32_t> tilePairs;
     for (int t = 0; t < d->numTiles; t++) {
         const int m0 = p->tileMolOffset[t], nMol = p->tileMolOffset[t + 1] - m0;
         int molFirst = nMol > 0 ? p->tileMolList[m0] : 0;
@@ -894,7 +1040,21 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
             if (p->tileMolList[m0 + j] != molFirst + j) molFirst = -1;
         int32_t *e = desc.data() + (size_t) t * 8;
         e[0] = p->tileStart[t]; e[1] = p->tileStart[t + 1]; e[2] = m0; e[3] = nMol; e[4] = molFirst;
+        e[5] = (int32_t) tilePairs.size();
+        if (p->tiled) {
+            const int a = p->tileStart[t], b = p->tileStart[t + 1];
+            for (int i = a; i < b; i++) {
+                const uint32_t mw = p->slotMeta[i];
+                if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
+                    continue;
+                const int partner = i + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+                tilePairs.push_back((uint32_t) (i - a) | ((uint32_t) (partner - a) << 16));
+            }
+        }
+        e[6] = (int32_t) tilePairs.size() - e[5];
+        while (tilePairs.size() % 4) tilePairs.push_back(0u);
     }
+    tilePairs.resize(tilePairs.size() + 8, 0u);
     molInfo.resize(molInfo.size() + 8, 0);                       // bulk copies read rounded-up ranges
     std::vector<uint32_t> metaPadded(p->slotMeta);
     metaPadded.resize((size_t) p->paddedN + 8, VVB200_META_MOL_NONE);
@@ -902,6 +1062,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     if ((rc = uploadVec(d, &d->tileDesc, desc.data(), (size_t) d->numTiles * 2, st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolList, p->tileMolList.data(), p->tileMolList.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolInfo, molInfo.data(), molInfo.size(), st))) return rc;
+    if ((rc = uploadVec(d, &d->tilePairs, tilePairs.data(), tilePairs.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->slotMeta, metaPadded.data(), metaPadded.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->sortedByMol, p->sortedByMol.data(), p->sortedByMol.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->particlesInMolecules, p->particlesInMolecules.data(), p->particlesInMolecules.size(), st))) return rc;
@@ -935,7 +1096,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
 
     // per-block partial sums: sized for the largest persistent grid any instantiation may use
     if ((rc = uploadVec(d, &d->partials, nullptr, (size_t) d->numSM * VVB200_MAX_BLOCKS_PER_SM * VVB200_NRED, st))) return rc;
-    if ((rc = uploadVec(d, &d->counter, nullptr, 2, st))) return rc;
+    if ((rc = uploadVec(d, &d->counter, nullptr, 192, st))) return rc;      // four words and the factor records, each on a 128-byte line of its own
     NhcDevice h;
     fillNhcHost(p, h);
     if ((rc = uploadVec(d, &d->nhc, &h, 1, st))) return rc;
@@ -1010,13 +1171,14 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.peerOn = 0;                 // set by the multi-GPU step calls when the peer exchange is attached
     k.peer = d->peer;
     k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
-    k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
+    k.tileMolInfo = d->tileMolInfo; k.tilePairs = d->tilePairs; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
     k.tileMolFrag = d->tileMolFrag; k.splitMolId = d->splitMolId; k.splitFragOffset = d->splitFragOffset;
     k.splitFragList = d->splitFragList; k.fragPartials = d->fragPartials; k.numSplit = (int) p->splitMolId.size();
     k.posq = b->posq; k.corr = b->posq_correction; k.velm = b->velm; k.force = b->force;
     k.ldForce = d->ldForce; k.comV = d->comV; k.comCbar = d->comCbar;
-    k.partials = d->partials; k.nhc = d->nhc; k.counter = d->counter; k.gridGen = d->counter + 1;
+    k.partials = d->partials; k.nhc = d->nhc; k.counter = d->counter; k.gridGen = d->counter + 32; k.syncFlag = d->counter + 64; k.tileTicket = d->counter + 96; k.tileReverse = d->tileReverse;
+    k.factorRec = reinterpret_cast<FactorRec *>(d->counter + 128);
     k.dt = p->par.step_size;
     k.efscale = p->par.electric_field * AVOGADRO_D;          // CudaVVKernels.cpp:978
     k.accel = p->par.cos_acceleration;                       // :1044
@@ -1158,6 +1320,12 @@ static cudaError_t launchB(KParams k, int numSM, cudaStream_t st) {
     k.stagesB = cfg.stages;
     const int grid = std::max(1, std::min(k.tileEnd - k.tileBegin, numSM * cfg.perSM));
     return launchStreaming(scale_drift_kernel<MODE, VARIANT, EXTRA>, grid, blockThreads, cfg.smem, st, k);
+}
+
+// Pass B of a call that launches both passes itself takes over from pass A through the hand-over word instead of waiting
+// for the whole grid (vvb200_stream.cuh, "early hand-over"); VVB200_HANDOVER=0 restores griddepcontrol.wait (tests).
+static int handOverFor(const vvb200_plan *p, const KParams &k) {
+    return p->dev->handOver && k.fuseNHC && !k.kickOnly ? 1 : 0;
 }
 
 // EXTRA kernels stage posq as well: needed by the external field (charge), the cosine acceleration (z) and, for
@@ -1660,6 +1828,7 @@ extern "C" int vvb200_step_middle(vvb200_plan *p, const vvb200_buffers *b, const
         k.peerOn = 1;
         k.fuseNHC = 1;
     }
+    k.flagSync = handOverFor(p, k);
     profMark(p->dev, 0, st);
     bool resident = false;
     if (!k.peerOn && (rc = tryResident<KICK_MIDDLE, VAR_MIDDLE>(p, k, hasNH(p), st, &resident))) return rc;
@@ -1704,6 +1873,8 @@ extern "C" int vvb200_step_vv_first(vvb200_plan *p, const vvb200_buffers *b, con
     if ((rc = tryResident<KICK_NONE, VAR_VV_FIRST>(p, k, hasNH(p), st, &resident))) return rc;
     if (resident)
         return k.imageFused ? VVB200_OK : vvb200_update_image_positions(p, b, stream);   // fused: pass B mirrored them
+    k.fuseNHC = hasNH(p);
+    k.flagSync = handOverFor(p, k);
     profMark(p->dev, 0, st);
     if (hasNH(p)) {
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
@@ -1736,6 +1907,7 @@ extern "C" int vvb200_step_vv_second(vvb200_plan *p, const vvb200_buffers *b, co
         if (resident)
             return VVB200_OK;
     }
+    k.flagSync = handOverFor(p, k);
     profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_VV>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
@@ -1783,6 +1955,7 @@ extern "C" int vvb200_thermostat(vvb200_plan *p, const vvb200_buffers *b, const 
     if ((rc = tryResident<KICK_NONE, VAR_SCALE_ONLY>(p, k, true, st, &resident))) return rc;
     if (resident)
         return VVB200_OK;
+    k.flagSync = handOverFor(p, k);
     profMark(p->dev, 0, st);
     CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
     p->launches++;
@@ -1837,6 +2010,7 @@ extern "C" int vvb200_middle_thermostat_delta(vvb200_plan *p, const vvb200_buffe
             profMark(p->dev, 3, st);
             return VVB200_OK;
         }
+        k.flagSync = handOverFor(p, k);
         CUDA_TRY((dispatchA<KICK_NONE>(p->precision, cosine, k, p->dev->numSM, st)));
         p->launches++;
     }
@@ -2189,6 +2363,9 @@ extern "C" int vvb200_measure_temperatures(vvb200_plan *p, const vvb200_buffers 
 #ifdef VVB200_TRACE
 extern "C" int vvb200_debug_trace(unsigned long long *out, int n) {
     return (int) cudaMemcpyFromSymbol(out, g_vvb200Trace, sizeof(unsigned long long) * n);
+}
+extern "C" int vvb200_debug_trace_streaming(unsigned long long *out, int n) {
+    return (int) cudaMemcpyFromSymbol(out, g_vvb200TraceS, sizeof(unsigned long long) * n);
 }
 #endif
 

@@ -39,6 +39,7 @@ __host__ __device__ constexpr int passBMinBlocks(int variant) { return variant =
 #define ITEMS ((VVB200_TILE_CAP + CTHREADS - 1) / CTHREADS)   // particles per consumer thread (the last round may be partial)
 #define PADT (VVB200_TILE_CAP + 8)            // stage slots: tile + alignment slack
 #define MAXMOL VVB200_TILE_MAX_MOLS
+#define MAXPAIRS (VVB200_TILE_CAP / 2)        // Drude pairs per tile
 static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
 
 // -DVVB200_TRACE (diagnostic builds only, tests/diag_trace.py): %globaltimer stamps of thread 0 of every block
@@ -51,8 +52,18 @@ __device__ __forceinline__ void traceMark(int i) {
         g_vvb200Trace[blockIdx.x * 8 + i] = t;
     }
 }
+// streaming kernels: one row per block and pass (rows 0..1023 pass A, 1024..2047 pass B), stamped by the calling thread
+__device__ unsigned long long g_vvb200TraceS[2048 * 8];
+__device__ __forceinline__ void traceMarkS(int pass, int i) {
+    if (blockIdx.x < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_vvb200TraceS[(pass * 1024 + blockIdx.x) * 8 + i] = t;
+    }
+}
 #else
 #define traceMark(i) ((void) 0)
+#define traceMarkS(pass, i) ((void) 0)
 #endif
 
 // ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------------------
@@ -92,8 +103,42 @@ __device__ __forceinline__ void gridDepWait() { asm volatile("griddepcontrol.wai
 __device__ __forceinline__ void gridDepLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void consumerBarrier() { asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory"); }
 
+// ---- early hand-over from pass A to pass B ------------------------------------------------------------------------
+// griddepcontrol.wait in pass B would wait for ALL of pass A: the last block's sum over the per-block partials, the whole
+// chain update, its write-back and the grid's completion -- 4-5 us in which the other 147 SMs have nothing to do, a
+// tenth of a 1M-particle step.  Pass B needs two things only: every tile's kicked velocities (done once the last
+// arrival ticket is taken) and the three scale factors (done after nhcCrit).  So
+//   * every block of pass A tells the runtime right after ITS OWN griddepcontrol.wait that dependents may be scheduled:
+//     pass B's blocks take over an SM as soon as pass A's blocks there have left (they cannot co-reside: registers),
+//     and since a dependent grid starts only after ALL blocks of pass A have said so, every block of pass A is resident
+//     or done by then -- a waiting pass B can never keep a block of pass A from running;
+//   * block 0 of pass A zeroes the hand-over word and the factor records before that (after its wait, i.e. after the
+//     previous pass B is completely done with them); the last block sets the word to 1 (velocities visible) and, right
+//     after nhcCrit, writes each factor as a self-validating 16-byte record (device.cu, FactorRec);
+//   * ONE thread per block of pass B polls the word (it has a 128-byte line to itself; thousands of pollers on the line
+//     of the arrival ticket slowed pass A's own tail down): the producer waits for >= 1 before its first bulk copy,
+//     and fills the ring; four lanes of the first consumer warp poll the factor records, put the values into shared
+//     memory and open a barrier the other warps sleep on (bounded waits: on expiry the factors are poisoned with NaN,
+//     the device never hangs);
+//   * pass B's blocks start at different times now (the SM that hosts pass A's last block comes last), so under the
+//     hand-over they draw their tiles from a counter instead of striding -- from the END of the system backwards: what
+//     pass A wrote last is what L2 still holds.  (Pass A keeps its static stride: its per-block partial sums must not
+//     depend on timing.)
+// p.flagSync is set by the entry points that launch both passes themselves; everything else keeps griddepcontrol.wait.
+__device__ __forceinline__ void passAHandOverStart(const KParams &p, const int tid) {
+    if (tid == 0) {
+        if (p.flagSync && blockIdx.x == 0) {
+            *p.tileTicket = 0u;
+            for (int k = 0; k < 4; k++) factorPublish(p.factorRec + k, 0.0, 0ull);
+            st_release_gpu(p.syncFlag, 0u);
+            __threadfence();
+        }
+        gridDepLaunch();
+    }
+}
+
 // tile descriptor (two int4 per tile, built by vvb200_plan_upload)
-//   d0 = (t0, t1, m0, nMol)   d1 = (molFirst or -1, 0, 0, 0)
+//   d0 = (t0, t1, m0, nMol)   d1 = (molFirst or -1, offset of the tile's pair list, number of pairs, 0)
 // molFirst >= 0: the tile's thermostat molecules are the consecutive ids molFirst .. molFirst+nMol-1
 
 template <int MODE, bool EXTRA, bool FORCE = true> struct StageA {      // FORCE = false: the reduce-only variant (KICK_NONE)
@@ -101,6 +146,7 @@ template <int MODE, bool EXTRA, bool FORCE = true> struct StageA {      // FORCE
     long long f[3][FORCE ? PADT : 2];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
+    uint32_t pairs[MAXPAIRS + 4];
     int32_t desc[8];
     typename Prec<MODE>::real4 posq[EXTRA ? PADT : 1];
 };
@@ -113,12 +159,14 @@ template <int MODE, bool EXTRA> struct PublishedA {
     mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], m[VVB200_TILE_CAP];
     double cph[EXTRA ? VVB200_TILE_CAP : 2];
     int32_t molInfo[MAXMOL];
+    uint32_t pairs[MAXPAIRS];
 };
 
 template <int MODE, bool EXTRA> struct ScratchA {
     typedef typename Prec<MODE>::mixed mixed;
     PublishedA<MODE, EXTRA> pub[2];
     double red[CTHREADS / 32][VVB200_NRED];
+    double nhcE0[4];                 // nhcPre's exponential per temperature group
     unsigned long long peerSeq;
     unsigned int ticket;
 };
@@ -333,6 +381,8 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
         }
     }
     if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
+    if (!p.kickOnly)
+        for (int j = tid; j < st.desc[6]; j += CTHREADS) pub.pairs[j] = st.pairs[j];
 }
 
 // ---- phases 2 and 3 (after a block barrier): molecular COM velocities, then the Drude pairs -----------
@@ -340,7 +390,8 @@ template <int MODE, bool EXTRA, bool RESIDENT, class Stage, int KICK = KICK_NONE
 __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> &cx, Stage &st, PublishedA<MODE, EXTRA> &pub,
                                              const typename Prec<MODE>::mixed4 (&vel)[ITEMS], const uint32_t (&meta)[ITEMS],
                                              typename Prec<MODE>::mixed (&acc)[EXTRA ? VVB200_NRED : 3], const int tid,
-                                             const int t0, const int t1, const int m0, const int nMol, const int molFirst) {
+                                             const int t0, const int t1, const int m0, const int nMol, const int molFirst,
+                                             const int nPairs) {
     typedef Prec<MODE> P;
     typedef typename P::mixed mixed;
     typedef typename P::mixed4 mixed4;
@@ -428,19 +479,15 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
         }
     }
 
-    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: the relative-motion energy
-    //      mu|v1 - v2|^2 is the Drude group's, and leaves the atom group (see phase 1) -------------------------------
-#pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        const uint32_t mw = meta[it];
-        if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
-            continue;
-        const int loc = it * CTHREADS + tid;
-        const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-        const mixed4 v = vel[it];     // .w = mass
-        const mixed mass1 = v.w, mass2 = pub.m[ploc];
+    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114): the relative-motion energy mu|v1 - v2|^2 is the Drude group's,
+    //      and leaves the atom group (see phase 1).  One pair per thread from the tile's dense pair list: a third of the
+    //      warp instructions of a phase that only the Drude particles' own lanes take part in. ------------------------
+    for (int j = tid; j < nPairs; j += CTHREADS) {
+        const uint32_t pw = pub.pairs[j];
+        const int loc = (int) (pw & 0xFFFFu), ploc = (int) (pw >> 16);
+        const mixed mass1 = pub.m[loc], mass2 = pub.m[ploc];
         const mixed redMass = mass1 * mass2 * rcpMass(mass1 + mass2);       // = 1 / ((m1+m2) w1 w2)
-        const mixed rx = v.x - pub.vx[ploc], ry = v.y - pub.vy[ploc], rz = v.z - pub.vz[ploc];
+        const mixed rx = pub.vx[loc] - pub.vx[ploc], ry = pub.vy[loc] - pub.vy[ploc], rz = pub.vz[loc] - pub.vz[ploc];
         const mixed e = (rx * rx + ry * ry + rz * rz) * redMass;
         acc[2] += e;
         acc[0] -= e;
@@ -460,6 +507,19 @@ __device__ __forceinline__ void nhcFetch(NhcDevice *shared, const NhcDevice *glo
     const int i = tid - first;
     if (i >= 0 && i < (int) (sizeof(NhcDevice) / 8))
         reinterpret_cast<double *>(shared)[i] = __ldcg(reinterpret_cast<const double *>(global) + i);
+}
+// the same by ONE warp (threads first .. first + 31), which then runs the part of the chain update that does not depend
+// on this step's kinetic energy (nhcPre, device.cu) while the block's first tiles are still in flight
+__device__ __forceinline__ void nhcFetchAndPre(NhcDevice *shared, const NhcDevice *global, double *e0, const double dt,
+                                               const int tid, const int first) {
+    const int lane = tid - first;
+    if (lane < 0 || lane >= 32)
+        return;
+    for (int i = lane; i < (int) (sizeof(NhcDevice) / 8); i += 32)
+        reinterpret_cast<double *>(shared)[i] = __ldcg(reinterpret_cast<const double *>(global) + i);
+    __syncwarp();
+    if (lane < 3)
+        e0[lane] = nhcPre(shared, lane, dt);
 }
 __device__ __forceinline__ void nhcStore(NhcDevice *global, const NhcDevice *shared, const int tid) {
     if (tid < (int) (sizeof(NhcDevice) / 8))
@@ -501,21 +561,47 @@ __device__ __forceinline__ bool blockReduceAndTicket(const KParams &p, Scratch &
 // back afterwards (resident kernel: saves the chain's serial L2 round trips).
 template <int MODE, int NR, class Scratch>
 __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, const bool cosine, const int tid,
-                                                NhcDevice *work = nullptr) {
+                                                NhcDevice *work = nullptr, const bool splitChain = false) {
+    // splitChain: the caller ran nhcPre on `work` (nhcFetchAndPre) -- the chain update goes on from there
     typedef typename Prec<MODE>::mixed mixed;
     typedef typename Prec<MODE>::mixed4 mixed4;
     if (!work) work = p.nhc;
     const int lane = tid & 31, warp = tid >> 5;
+    // every block has stored its velocities (and whole molecules' centre-of-mass velocities) and taken its ticket:
+    // pass B's producers may start loading (split molecules: after their centre of mass below).  The fence makes the
+    // ticket chain an acquire for this block's loads of the partials and, with the store after it, a release for the word.
     __threadfence();
+    if (p.flagSync && p.numSplit == 0 && tid == 0)
+        *reinterpret_cast<volatile unsigned int *>(p.syncFlag) = 1u;      // fence + store = release: ONE fence on this path
+    if (tid == 0) traceMarkS(0, 2);
     // all NR sums of a block's partials are fetched together (independent loads: one L2 round trip per block row)
     double tot[NR];
 #pragma unroll
     for (int k = 0; k < NR; k++) tot[k] = 0;
-    for (int b = tid; b < (int) gridDim.x; b += CTHREADS) {
+    // (the first rounds unrolled: their loads are independent and leave together -- one L2 round trip, not one per round)
+    {
+        double part[3][NR];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int b = tid + r * CTHREADS;
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                part[r][k] = b < (int) gridDim.x ? __ldcg(p.partials + (size_t) b * VVB200_NRED + k) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            if (tid + r * CTHREADS < (int) gridDim.x) {
+#pragma unroll
+                for (int k = 0; k < NR; k++) tot[k] += part[r][k];
+            }
+        }
+    }
+    for (int b = tid + 3 * CTHREADS; b < (int) gridDim.x; b += CTHREADS) {
 #pragma unroll
         for (int k = 0; k < NR; k++)
             tot[k] += __ldcg(p.partials + (size_t) b * VVB200_NRED + k);
     }
+    if (tid == 0) traceMarkS(0, 3);
     // molecules cut across tiles: add their fragments up in tile order, finish the centre of mass the way phase 2 does
     // for whole molecules (drudeNoseHoover.cu:11-30, 91-97) and move M|V|^2 from the atom group to the molecular group
     // (a step cut into several launches over tile ranges -- the host pipeline -- finishes them once, in the launch that
@@ -560,8 +646,13 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
         work->red[tid] = v;
         sm.red[0][tid] = v;      // thread `tid` is the only reader of column `tid`
     }
-    if (tid == 0)
+    if (tid == 0) {
         *p.counter = 0;
+        if (p.flagSync && p.numSplit != 0) {      // the barrier above ordered every thread's comV stores before this
+            __threadfence();
+            st_release_gpu(p.syncFlag, 1u);
+        }
+    }
     consumerBarrier();
     if (p.peerOn) {
         // multi-GPU: this rank's sums are final -- exchange them with the peers over NVLink right here (device.cu,
@@ -585,10 +676,25 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
     }
 #ifdef VVB200_TRACE
     traceMark(7);
+    if (tid == 0) traceMarkS(0, 7);
 #endif
     if (p.fuseNHC && tid < 3) {
-        if (cosine) nhcFinish<true>(work, p.dt, tid, sm.red[0]);
-        else nhcFinish<false>(work, p.dt, tid, sm.red[0]);
+        if (!splitChain) {
+            if (cosine) nhcFinish<true>(work, p.dt, tid, sm.red[0]);
+            else nhcFinish<false>(work, p.dt, tid, sm.red[0]);
+        } else {
+            const double e0 = sm.nhcE0[tid];
+            if (cosine) nhcCrit<true>(work, p.dt, tid, sm.red[0], e0);
+            else nhcCrit<false>(work, p.dt, tid, sm.red[0], e0);
+            // what pass B needs leaves right now, each factor in a self-validating record (no fence, no second word);
+            // the state itself follows with nhcStore once the rest of the chain update is done
+            if (p.flagSync) {
+                factorPublish(p.factorRec + tid, work->vscale[tid], 1ull);
+                if (tid == 0) factorPublish(p.factorRec + 3, work->vBias, 1ull);
+            }
+            if (tid == 0) traceMarkS(0, 5);
+            nhcPost(work, p.dt, tid, e0);
+        }
     }
 }
 
@@ -619,7 +725,10 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
         fenceBarrierInit();
     }
     __syncthreads();
+    if (tid == 0) traceMarkS(0, 0);
     gridDepWait();      // PDL: everything above overlapped the previous kernel's tail (pass B of the step before)
+    if (tid == 0) traceMarkS(0, 1);
+    passAHandOverStart(p, tid);
 
     const bool cosine = EXTRA && p.cosine;
     const bool useCOM = p.useCOM;
@@ -636,11 +745,14 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
             const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
             const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
+            const int pcnt = p.kickOnly ? 0 : (d1.z + 3) & ~3;
             st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
-            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u;
+            st.desc[6] = p.kickOnly ? 0 : d1.z;
+            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u + pcnt * 4u;
             if (KICK != KICK_NONE) bytes += 3u * cnt * 8u;
             if (EXTRA) bytes += cnt * (uint32_t) sizeof(real4);
             mbarArriveExpectTx(full + s, bytes);
+            if (pcnt) bulkLoad(st.pairs, p.tilePairs + d1.y, pcnt * 4u, full + s);
             bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
             if (KICK != KICK_NONE) {
                 bulkLoad(st.f[0], p.force + a0, cnt * 8u, full + s);
@@ -659,7 +771,7 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
     // every block prefetches the thermostat state (any of them may arrive last): the chains then run on shared memory
     // instead of a string of dependent L2 round trips
     if (p.fuseNHC)
-        nhcFetch(&nhcS, p.nhc, tid, 0);
+        nhcFetchAndPre(&nhcS, p.nhc, sm.nhcE0, p.dt, tid, 0);
     const ACtx<MODE> c = makeACtx<MODE, KICK>(p, EXTRA);
     constexpr int NR = EXTRA ? VVB200_NRED : 3;
     // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
@@ -671,9 +783,11 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
     uint32_t phase = 0;
     for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
         mbarWait(full + s, phase);
+        if (tid == 0 && tile == p.tileBegin + (int) blockIdx.x) traceMarkS(0, 2);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
         PublishedA<MODE, EXTRA> &pub = sm.pub[buf];
         const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
+        const int nPairs = st.desc[6];
         mixed4 vel[ITEMS];
         uint32_t meta[ITEMS];
         passAPhase1<MODE, KICK, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid);
@@ -684,17 +798,21 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
             continue;
         }
         consumerBarrier();
-        passAPhase23<MODE, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst);
+        passAPhase23<MODE, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst, nPairs);
         buf ^= 1;
     }
 
-    if (tid == 0) gridDepLaunch();      // this block's tiles are done: pass B may start being scheduled
-    if (!blockReduceAndTicket<NR>(p, sm, acc, tid))
+    if (tid == 0) traceMarkS(0, 3);
+    if (!blockReduceAndTicket<NR>(p, sm, acc, tid)) {
+        if (tid == 0) traceMarkS(0, 4);
         return;
+    }
+    if (tid == 0) traceMarkS(0, 4);
     if (p.fuseNHC) {
-        lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS);
+        lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS, true);
         consumerBarrier();
         nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
+        if (tid == 0) traceMarkS(0, 6);
     } else {
         lastBlockFinish<MODE, NR>(p, sm, cosine, tid);
     }
@@ -722,10 +840,12 @@ template <int MODE> struct StageRed {
     typename Prec<MODE>::mixed4 velm[PADT];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
+    uint32_t pairs[MAXPAIRS + 4];
     int32_t desc[8];
 };
 struct ScratchRed {
     double red[CTHREADS / 32][VVB200_NRED];
+    double nhcE0[4];
     unsigned long long peerSeq;
     unsigned int ticket;
 };
@@ -759,6 +879,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
     }
     __syncthreads();
     gridDepWait();
+    passAHandOverStart(p, tid);
     const bool useCOM = p.useCOM;
 
     if (tid >= CTHREADS) {
@@ -773,8 +894,10 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
             const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
             const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
-            st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
-            mbarArriveExpectTx(full + s, cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u);
+            const int pcnt = (d1.z + 3) & ~3;
+            st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x; st.desc[6] = d1.z;
+            mbarArriveExpectTx(full + s, cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u + pcnt * 4u);
+            if (pcnt) bulkLoad(st.pairs, p.tilePairs + d1.y, pcnt * 4u, full + s);
             bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
             bulkLoad(st.meta, p.slotMeta + a0, cnt * 4u, full + s);
             if (mcnt) bulkLoad(st.molInfo, p.tileMolInfo + ma0, mcnt * 4u, full + s);
@@ -785,7 +908,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
 
     // ===== consumers =====
     if (p.fuseNHC)
-        nhcFetch(&nhcS, p.nhc, tid, 0);
+        nhcFetchAndPre(&nhcS, p.nhc, sm.nhcE0, p.dt, tid, 0);
     mixed acc[3] = {0, 0, 0};
     mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
     int s = 0;
@@ -796,26 +919,15 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
         const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
         const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
         const mixed4 *sv = st.velm + sl0;      // (vx, vy, vz, 1/m) per tile-local slot
-        // ---- per particle: m|v|^2 of every massive thermostat particle (see passAPhase1) and, on the Drude's lane, the
-        //      pair's relative-motion energy mu|v1 - v2|^2 (drudeNoseHoover.cu:99-114) ----
-        mixed pairRel[ITEMS];
+        // ---- per particle: m|v|^2 of every massive thermostat particle (see passAPhase1) ----
 #pragma unroll
         for (int it = 0; it < ITEMS; it++) {
             const int loc = it * CTHREADS + tid;
-            pairRel[it] = 0;
             if (t0 + loc < t1) {
                 const mixed4 v = sv[loc];
                 const uint32_t mw = st.meta[sl0 + loc];
-                const mixed mass = v.w != 0 ? rcpMass(v.w) : (mixed) 0;
                 if ((mw & VVB200_META_NH) && v.w != 0)
-                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
-                if ((mw & VVB200_META_NH) && ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_DRUDE) {
-                    const mixed4 q = sv[loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS];
-                    const mixed mass2 = rcpMass(q.w);
-                    const mixed redMass = mass * mass2 * rcpMass(mass + mass2);
-                    const mixed rx = v.x - q.x, ry = v.y - q.y, rz = v.z - q.z;
-                    pairRel[it] = (rx * rx + ry * ry + rz * rz) * redMass;
-                }
+                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * rcpMass(v.w);
             }
         }
         // ---- molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), COM_LANES lanes per molecule ----
@@ -871,21 +983,26 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
                 }
             }
         }
+        // ---- Drude pairs (drudeNoseHoover.cu:99-114): mu|v1 - v2|^2, one pair of the tile's dense list per thread, after
+        //      the molecule terms -- the order and the thread pass A adds them in (bit-identical sums) ----
+        for (int j = tid; j < st.desc[6]; j += CTHREADS) {
+            const uint32_t pw = st.pairs[j];
+            const mixed4 v = sv[pw & 0xFFFFu], q = sv[pw >> 16];
+            const mixed mass1 = rcpMass(v.w), mass2 = rcpMass(q.w);
+            const mixed redMass = mass1 * mass2 * rcpMass(mass1 + mass2);
+            const mixed rx = v.x - q.x, ry = v.y - q.y, rz = v.z - q.z;
+            const mixed e = (rx * rx + ry * ry + rz * rz) * redMass;
+            acc[2] += e;
+            acc[0] -= e;
+        }
         mbarArrive(empty + s);      // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
-        // the pair terms join the sums AFTER the molecule terms: the order pass A adds them in (bit-identical sums)
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            acc[2] += pairRel[it];
-            acc[0] -= pairRel[it];
-        }
     }
 
-    if (tid == 0) gridDepLaunch();
     if (!blockReduceAndTicket<3>(p, sm, acc, tid))
         return;
     if (p.fuseNHC) {
-        lastBlockFinish<MODE, 3>(p, sm, false, tid, &nhcS);
+        lastBlockFinish<MODE, 3>(p, sm, false, tid, &nhcS, true);
         consumerBarrier();
         nhcStore(p.nhc, &nhcS, tid);
     } else {
@@ -953,7 +1070,8 @@ template <int MODE> struct BCtx {
 };
 
 // `nhc` values are read through L2 (__ldcg): in the resident kernel another block wrote them during this launch
-template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams &p, bool extra) {
+// `fac`: the factors as pass B's producer received them (hand-over); nullptr: from the thermostat state
+template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams &p, bool extra, const double *fac = nullptr) {
     typedef typename Prec<MODE>::real real;
     typedef typename Prec<MODE>::mixed mixed;
     BCtx<MODE> c;
@@ -964,10 +1082,17 @@ template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams
     c.halfdt = 0.5f * c.stepSize;                       // middle.cu:33,51
     c.invStepSize = (mixed) (1.0 / c.stepSize);         // velocityVerlet.cu:40
     c.fscaleVV = (mixed) (0.5 * p.dt / (double) 0x100000000);
-    c.sA = (mixed) __ldcg(&p.nhc->vscale[0]);
-    c.sC = (mixed) __ldcg(&p.nhc->vscale[1]);
-    c.sD = (mixed) __ldcg(&p.nhc->vscale[2]);
-    c.Vb = c.cosine ? (mixed) __ldcg(&p.nhc->vBias) : (mixed) 0;
+    if (fac) {
+        c.sA = (mixed) fac[0];
+        c.sC = (mixed) fac[1];
+        c.sD = (mixed) fac[2];
+        c.Vb = c.cosine ? (mixed) fac[3] : (mixed) 0;
+    } else {
+        c.sA = (mixed) __ldcg(&p.nhc->vscale[0]);
+        c.sC = (mixed) __ldcg(&p.nhc->vscale[1]);
+        c.sD = (mixed) __ldcg(&p.nhc->vscale[2]);
+        c.Vb = c.cosine ? (mixed) __ldcg(&p.nhc->vBias) : (mixed) 0;
+    }
     c.maxD = (mixed) p.maxDrudeDistance;
     // conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold
     c.maxD2safe = (real) (p.maxDrudeDistance * p.maxDrudeDistance * (1.0 - 1e-4));
@@ -1375,6 +1500,9 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
     constexpr size_t stageBytes = roundUp128(sizeof(Stage));
     uint64_t *full = reinterpret_cast<uint64_t *>(smemRaw + stageBytes * stages);
     uint64_t *empty = full + stages;
+    uint64_t *ready = empty + stages;       // hand-over: opened by the producer once the scale factors are published
+    __shared__ int expiredS;
+    __shared__ double facS[4];
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -1382,10 +1510,16 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
             mbarInit(full + s, 1);
             mbarInit(empty + s, CTHREADS_B);
         }
+        mbarInit(ready, 1);
         fenceBarrierInit();
+        expiredS = 0;
     }
     __syncthreads();
-    gridDepWait();      // PDL: everything above overlapped pass A's last-block reduction and NH chains
+    // PDL: everything above overlapped pass A's tail.  With the hand-over word this block goes on as soon as what it
+    // needs exists (see "early hand-over"); otherwise it waits for the whole preceding grid.
+    const bool handOver = p.flagSync && VARIANT != VAR_FINISH && VARIANT != VAR_VV_POSITIONS;
+    if (tid == 0) traceMarkS(1, 0);
+    if (!handOver) gridDepWait();
 
     const bool cosine = EXTRA && p.cosine;
     const bool useCOM = p.useCOM && VARIANT != VAR_FINISH && VARIANT != VAR_VV_POSITIONS;   // these two do not touch the thermostat
@@ -1395,9 +1529,41 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
         const int lane = tid - CTHREADS_B;
         const mixed4 *comV = reinterpret_cast<const mixed4 *>(p.comV);
         const mixed *comCbar = reinterpret_cast<const mixed *>(p.comCbar);
+        if (handOver) {
+            // pass A's velocities and centre-of-mass velocities must be visible before the first copy is issued; the
+            // copies run in the async proxy, hence the proxy fence after the acquire
+            if (lane == 0) waitFlagAtLeast(p.syncFlag, 1u);
+            __syncwarp();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (lane == 0) traceMarkS(1, 1);
+        }
         int s = 0;
         uint32_t phase = 0;
-        for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
+        // hand-over: tiles come from a shared counter.  The ticket for the NEXT round is requested before this round's
+        // copies are issued, so the atomic's round trip is never on the producer's critical path (a producer that
+        // draws, waits, reads the descriptor, waits, issues needs longer per tile than the consumers do).
+        int nextTicket = 0;
+        if (handOver && lane == 0) nextTicket = (int) atomicAdd(p.tileTicket, 1u);
+        for (int tile = p.tileBegin + blockIdx.x;; tile += gridDim.x) {
+            if (handOver) {
+                int t = nextTicket;
+                if (lane == 0) nextTicket = (int) atomicAdd(p.tileTicket, 1u);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                // last tile first: what pass A wrote last is what L2 still holds
+                tile = p.tileReverse ? p.tileEnd - 1 - t : p.tileBegin + t;
+                const bool none = t >= p.tileEnd - p.tileBegin;
+                if (none) {
+                    // end mark for the consumers: an empty stage whose descriptor says so
+                    mbarWait(empty + s, phase ^ 1);
+                    if (lane == 0) {
+                        reinterpret_cast<Stage *>(smemRaw + stageBytes * s)->desc[0] = -1;
+                        mbarArrive(full + s);
+                    }
+                    break;
+                }
+            } else if (tile >= p.tileEnd) {
+                break;
+            }
             const int4 d0 = __ldg(p.tileDesc + 2 * tile), d1 = __ldg(p.tileDesc + 2 * tile + 1);
             mbarWait(empty + s, phase ^ 1);
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
@@ -1452,15 +1618,43 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
     }
 
     // ===== consumers =====
-    const BCtx<MODE> cx = makeBCtx<MODE>(p, EXTRA);
+    if (handOver) {
+        // lanes 0..3 of the first consumer warp each poll one factor record (the producer is busy filling the ring) and
+        // hand the value to everybody through shared memory; the other warps sleep on the barrier
+        if (tid < 4) {
+            double v = 0;
+            const long long c0 = clock64();
+            while (!factorPoll(p.factorRec + tid, 1ull, &v)) {
+                if (clock64() - c0 > 4000000000LL) { expiredS = 1; break; }
+                __nanosleep(20);
+            }
+            facS[tid] = v;
+        }
+        if (tid < 32) {
+            __syncwarp();
+            if (tid == 0) mbarArrive(ready);
+        }
+        mbarWait(ready, 0);
+    }
+    if (tid == 0) traceMarkS(1, 2);
+    BCtx<MODE> cx = makeBCtx<MODE>(p, EXTRA, handOver ? facS : nullptr);
+    if (handOver && expiredS) {
+        const mixed nan = (mixed) __longlong_as_double(0x7ff8000000000000LL);
+        cx.sA = cx.sC = cx.sD = nan;
+    }
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
+    for (int tile = p.tileBegin + blockIdx.x; handOver || tile < p.tileEnd; tile += gridDim.x) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
+#ifdef VVB200_TRACE
+        if (tid == 0 && g_vvb200TraceS[(1024 + blockIdx.x) * 8 + 3] < g_vvb200TraceS[(1024 + blockIdx.x) * 8 + 0]) traceMarkS(1, 3);
+#endif
+        if (handOver && st.desc[0] < 0) break;      // the producer's end mark
         passBTile<MODE, VARIANT, EXTRA, CTHREADS_B>(p, cx, st, tid);
         mbarArrive(empty + s);   // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
     }
+    if (tid == 0) traceMarkS(1, 4);
     if (tid == 0) gridDepLaunch();      // the next kernel in the stream (next step's pass A) may be scheduled
 }

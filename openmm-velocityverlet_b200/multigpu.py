@@ -102,11 +102,14 @@ class DistributedPlan:
 
     def step_middle(self, bufs, **kw):
         import torch.distributed as dist
+        if self.peer:
+            # the LAST BLOCK OF PASS A exchanges the sums over cudaIpc-mapped NVLink memory and advances the chains; pass B
+            # takes over through the hand-over word -- the same two launches per step, the same call, as on one GPU
+            self.plan.step_middle(bufs, **kw)
+            return
         self.plan.middle_kick_reduce(bufs, **kw)
-        if not self.peer and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self._red, group=self.group)           # NCCL: the only exchange, <= 10 doubles
-        # peer path: the LAST BLOCK OF PASS A exchanged the sums over cudaIpc-mapped NVLink memory and advanced the chains;
-        # what follows is pass B alone -- the same two launches per step as on one GPU
         self.plan.middle_nhc_scale_drift(bufs, **kw)
 
     def step_host(self, host_state, **kw):

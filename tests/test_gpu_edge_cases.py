@@ -313,19 +313,62 @@ def test_edl_step_is_one_launch(vv, vo, step_path):
 def test_launch_overlap_changes_nothing(vv, vo, monkeypatch):
     """programmatic dependent launch (each streaming kernel is scheduled while its predecessor drains and waits at
     griddepcontrol.wait before touching data): 1,500 steps of a 220k-particle box with it on and off end bitwise
-    identical -- a kernel that started reading early would show up here"""
+    identical -- a kernel that started reading early would show up here.  Same for the early hand-over (pass B does not
+    wait for the whole of pass A but for a device word its last block sets: VVB200_HANDOVER), in every combination."""
     spec = vv.make_bulk_ionic_liquid(6000)
     params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
     host = vv.make_state(spec, "mixed", force_sigma=1.0)
     monkeypatch.setenv("VVB200_RESIDENT", "0")
     outs = []
-    for pdl in ("1", "0"):
+    for pdl, hand in (("1", "1"), ("0", "0"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("VVB200_PDL", pdl)
+        monkeypatch.setenv("VVB200_HANDOVER", hand)
         plan = vv.Plan(spec, params, "mixed").upload()
         bufs = vv.DeviceBuffers(host)
         plan.step(bufs, steps=1500)
         assert plan.launch_count == 3000
         outs.append((bufs.to_host(), plan.thermostat_state()))
-    (a, sa), (b, sb) = outs
+    (a, sa) = outs[0]
+    for b, sb in outs[1:]:
+        assert np.array_equal(a.velm, b.velm) and np.array_equal(a.posq, b.posq) and np.array_equal(a.corr, b.corr)
+        assert np.array_equal(sa["eta_dot"], sb["eta_dot"]) and np.array_equal(sa["eta"], sb["eta"])
+    assert np.isfinite(a.velm).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flow", ["vv", "constrained", "thermostat", "cosine", "polymer"])
+def test_hand_over_changes_nothing_in_any_flow(vv, monkeypatch, flow):
+    """the early hand-over in every entry point that uses it (velocity-Verlet halves, thermostat + deltas, thermostat
+    alone), with the cosine moments and with molecules cut across tiles (whose centre of mass the LAST block finishes
+    before pass B may load it): bitwise equal to waiting for the whole grid"""
+    import dataclasses
+    monkeypatch.setenv("VVB200_RESIDENT", "0")
+    if flow == "polymer":
+        spec = vv.make_polymer(n_chains=6, chain_len=3000, n_solvent=200, adjacent=True)
+    else:
+        spec = vv.make_bulk_ionic_liquid(5000)
+    params = vv.Params(max_drude_distance=0.02, cos_acceleration=0.02 if flow == "cosine" else 0.0).resolved_for(spec)
+    if flow == "vv":
+        params = dataclasses.replace(params, use_middle_scheme=False)
+    host = vv.make_state(spec, "mixed", force_sigma=1.0)
+    inv_box_z = 1.0 / host.box[2] if flow == "cosine" else 0.0
+    outs = []
+    for hand in ("1", "0"):
+        monkeypatch.setenv("VVB200_HANDOVER", hand)
+        plan = vv.Plan(spec, params, "mixed").upload()
+        bufs = vv.DeviceBuffers(host, with_pos_delta=True)
+        for _ in range(200):
+            if flow == "constrained":
+                plan.middle_kick(bufs)
+                plan.middle_thermostat_delta(bufs)
+                plan.middle_finish(bufs)
+            elif flow == "thermostat":
+                plan.middle_kick(bufs)
+                plan.thermostat(bufs)
+            else:
+                plan.step(bufs, steps=1, inv_box_z=inv_box_z)
+        outs.append((bufs.to_host(), plan.thermostat_state(), plan.com_velocities()))
+    (a, sa, ca), (b, sb, cb) = outs
     assert np.array_equal(a.velm, b.velm) and np.array_equal(a.posq, b.posq) and np.array_equal(a.corr, b.corr)
-    assert np.array_equal(sa["eta_dot"], sb["eta_dot"]) and np.isfinite(a.velm).all()
+    assert np.array_equal(sa["eta_dot"], sb["eta_dot"]) and np.array_equal(sa["vscale"], sb["vscale"]) and np.array_equal(ca, cb)
+    assert np.isfinite(a.velm).all()
