@@ -167,7 +167,6 @@ struct KParams {
     int N, paddedN, numTiles;
     const int4 *tileDesc;                      // 2 x int4 per tile, see vvb200_stream.cuh
     const int32_t *tileMolList, *tileMolInfo;
-    const uint32_t *tilePairs;                 // per tile: its thermostatted Drude pairs, (Drude slot) | (parent slot) << 16, tile-local
     const uint32_t *slotMeta;
     const int32_t *ldSlot;
     const int32_t *sortedByMol, *particlesInMolecules;
@@ -868,7 +867,6 @@ struct vvb200_device_state {
     int numTiles = 0;
     int4 *tileDesc = nullptr;
     int32_t *tileMolList = nullptr, *tileMolInfo = nullptr;
-    uint32_t *tilePairs = nullptr;
     int stagesA = 0, stagesB = 0, blocksPerSM = 0;   // 0: chosen per kernel from the shared-memory budget
     uint32_t *slotMeta = nullptr;
     int32_t *ldSlot = nullptr, *normalLD = nullptr, *sortedByMol = nullptr, *particlesInMolecules = nullptr;
@@ -1027,12 +1025,8 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
             }
         }
     }
-    // tile descriptors: (t0, t1, m0, nMol), (molFirst or -1, pair offset, pair count, 0)
-    // The thermostatted Drude pairs of a tile as a dense list, so that the pair phase of the reductions runs on
-    // consecutive lanes (one pair per thread) instead of on the one lane in three that happens to hold a Drude particle:
-    // tile-local slots (Drude | parent << 16), each tile's list padded to a multiple of 4 entries for the bulk copies.
+    // tile descriptors: (t0, t1, m0, nMol), (molFirst or -1, 0, 0, 0)
     std::vector<int32_t> desc((size_t) d->numTiles * 8, 0);
-    std::vector<uint32_t> tilePairs;
     for (int t = 0; t < d->numTiles; t++) {
         const int m0 = p->tileMolOffset[t], nMol = p->tileMolOffset[t + 1] - m0;
         int molFirst = nMol > 0 ? p->tileMolList[m0] : 0;
@@ -1040,21 +1034,7 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
             if (p->tileMolList[m0 + j] != molFirst + j) molFirst = -1;
         int32_t *e = desc.data() + (size_t) t * 8;
         e[0] = p->tileStart[t]; e[1] = p->tileStart[t + 1]; e[2] = m0; e[3] = nMol; e[4] = molFirst;
-        e[5] = (int32_t) tilePairs.size();
-        if (p->tiled) {
-            const int a = p->tileStart[t], b = p->tileStart[t + 1];
-            for (int i = a; i < b; i++) {
-                const uint32_t mw = p->slotMeta[i];
-                if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
-                    continue;
-                const int partner = i + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
-                tilePairs.push_back((uint32_t) (i - a) | ((uint32_t) (partner - a) << 16));
-            }
-        }
-        e[6] = (int32_t) tilePairs.size() - e[5];
-        while (tilePairs.size() % 4) tilePairs.push_back(0u);
     }
-    tilePairs.resize(tilePairs.size() + 8, 0u);
     molInfo.resize(molInfo.size() + 8, 0);                       // bulk copies read rounded-up ranges
     std::vector<uint32_t> metaPadded(p->slotMeta);
     metaPadded.resize((size_t) p->paddedN + 8, VVB200_META_MOL_NONE);
@@ -1062,7 +1042,6 @@ extern "C" int vvb200_plan_upload(vvb200_plan *p, void *stream) {
     if ((rc = uploadVec(d, &d->tileDesc, desc.data(), (size_t) d->numTiles * 2, st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolList, p->tileMolList.data(), p->tileMolList.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->tileMolInfo, molInfo.data(), molInfo.size(), st))) return rc;
-    if ((rc = uploadVec(d, &d->tilePairs, tilePairs.data(), tilePairs.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->slotMeta, metaPadded.data(), metaPadded.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->sortedByMol, p->sortedByMol.data(), p->sortedByMol.size(), st))) return rc;
     if ((rc = uploadVec(d, &d->particlesInMolecules, p->particlesInMolecules.data(), p->particlesInMolecules.size(), st))) return rc;
@@ -1171,7 +1150,7 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.peerOn = 0;                 // set by the multi-GPU step calls when the peer exchange is attached
     k.peer = d->peer;
     k.tileDesc = d->tileDesc; k.tileMolList = d->tileMolList;
-    k.tileMolInfo = d->tileMolInfo; k.tilePairs = d->tilePairs; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
+    k.tileMolInfo = d->tileMolInfo; k.slotMeta = d->slotMeta; k.ldSlot = d->ldSlot;
     k.sortedByMol = d->sortedByMol; k.particlesInMolecules = d->particlesInMolecules;
     k.tileMolFrag = d->tileMolFrag; k.splitMolId = d->splitMolId; k.splitFragOffset = d->splitFragOffset;
     k.splitFragList = d->splitFragList; k.fragPartials = d->fragPartials; k.numSplit = (int) p->splitMolId.size();

@@ -28,7 +28,6 @@ template <int MODE, int KICK, int VARIANT, bool EXTRA> struct StageR {
     typename Prec<MODE>::mixed4 comV[MAXMOL];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
-    uint32_t pairs[MAXPAIRS + 4];
     int32_t desc[8];
     typename Prec<MODE>::real4 posq[POSQ ? PADT : 1];
     typename Prec<MODE>::real4 corr[CORR ? PADT : 1];
@@ -86,11 +85,9 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * j);
             const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
             const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
-            const int pcnt = (d1.z + 3) & ~3;
             st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
             st.desc[5] = 0;                     // st.cbar is indexed by the tile-local molecule id
-            st.desc[6] = d1.z;
-            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u + pcnt * 4u;
+            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u;
             if (Stage::FORCE) bytes += 3u * cnt * 8u;
             if (Stage::POSQ) bytes += cnt * (uint32_t) sizeof(real4);
             if (Stage::CORR) bytes += cnt * (uint32_t) sizeof(real4);
@@ -103,7 +100,6 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             }
             bulkLoad(st.meta, p.slotMeta + a0, cnt * 4u, full + j);
             if (mcnt) bulkLoad(st.molInfo, p.tileMolInfo + ma0, mcnt * 4u, full + j);
-            if (pcnt) bulkLoad(st.pairs, p.tilePairs + d1.y, pcnt * 4u, full + j);
             if (Stage::POSQ) bulkLoad(st.posq, reinterpret_cast<const real4 *>(p.posq) + a0, cnt * (uint32_t) sizeof(real4), full + j);
             if (Stage::CORR) bulkLoad(st.corr, reinterpret_cast<const real4 *>(p.corr) + a0, cnt * (uint32_t) sizeof(real4), full + j);
         }
@@ -133,7 +129,7 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             uint32_t meta[ITEMS];
             passAPhase1<MODE, KICK, EXTRA, true>(p, ca, st, pub, vel, meta, acc, tid);
             consumerBarrier();
-            passAPhase23<MODE, EXTRA, true, Stage, KICK>(p, ca, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst, st.desc[6]);
+            passAPhase23<MODE, EXTRA, true, Stage, KICK>(p, ca, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst);
             buf ^= 1;
         }
     }

@@ -39,7 +39,6 @@ __host__ __device__ constexpr int passBMinBlocks(int variant) { return variant =
 #define ITEMS ((VVB200_TILE_CAP + CTHREADS - 1) / CTHREADS)   // particles per consumer thread (the last round may be partial)
 #define PADT (VVB200_TILE_CAP + 8)            // stage slots: tile + alignment slack
 #define MAXMOL VVB200_TILE_MAX_MOLS
-#define MAXPAIRS (VVB200_TILE_CAP / 2)        // Drude pairs per tile
 static_assert(VVB200_TILE_CAP <= 1024, "11-bit tile-local molecule ids");
 
 // -DVVB200_TRACE (diagnostic builds only, tests/diag_trace.py): %globaltimer stamps of thread 0 of every block
@@ -138,7 +137,7 @@ __device__ __forceinline__ void passAHandOverStart(const KParams &p, const int t
 }
 
 // tile descriptor (two int4 per tile, built by vvb200_plan_upload)
-//   d0 = (t0, t1, m0, nMol)   d1 = (molFirst or -1, offset of the tile's pair list, number of pairs, 0)
+//   d0 = (t0, t1, m0, nMol)   d1 = (molFirst or -1, 0, 0, 0)
 // molFirst >= 0: the tile's thermostat molecules are the consecutive ids molFirst .. molFirst+nMol-1
 
 template <int MODE, bool EXTRA, bool FORCE = true> struct StageA {      // FORCE = false: the reduce-only variant (KICK_NONE)
@@ -146,7 +145,6 @@ template <int MODE, bool EXTRA, bool FORCE = true> struct StageA {      // FORCE
     long long f[3][FORCE ? PADT : 2];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
-    uint32_t pairs[MAXPAIRS + 4];
     int32_t desc[8];
     typename Prec<MODE>::real4 posq[EXTRA ? PADT : 1];
 };
@@ -159,7 +157,6 @@ template <int MODE, bool EXTRA> struct PublishedA {
     mixed vx[VVB200_TILE_CAP], vy[VVB200_TILE_CAP], vz[VVB200_TILE_CAP], m[VVB200_TILE_CAP];
     double cph[EXTRA ? VVB200_TILE_CAP : 2];
     int32_t molInfo[MAXMOL];
-    uint32_t pairs[MAXPAIRS];
 };
 
 template <int MODE, bool EXTRA> struct ScratchA {
@@ -381,8 +378,6 @@ __device__ __forceinline__ void passAPhase1(const KParams &p, const ACtx<MODE> &
         }
     }
     if (tid < nMol) pub.molInfo[tid] = st.molInfo[ml0 + tid];
-    if (!p.kickOnly)
-        for (int j = tid; j < st.desc[6]; j += CTHREADS) pub.pairs[j] = st.pairs[j];
 }
 
 // ---- phases 2 and 3 (after a block barrier): molecular COM velocities, then the Drude pairs -----------
@@ -390,8 +385,7 @@ template <int MODE, bool EXTRA, bool RESIDENT, class Stage, int KICK = KICK_NONE
 __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> &cx, Stage &st, PublishedA<MODE, EXTRA> &pub,
                                              const typename Prec<MODE>::mixed4 (&vel)[ITEMS], const uint32_t (&meta)[ITEMS],
                                              typename Prec<MODE>::mixed (&acc)[EXTRA ? VVB200_NRED : 3], const int tid,
-                                             const int t0, const int t1, const int m0, const int nMol, const int molFirst,
-                                             const int nPairs) {
+                                             const int t0, const int t1, const int m0, const int nMol, const int molFirst) {
     typedef Prec<MODE> P;
     typedef typename P::mixed mixed;
     typedef typename P::mixed4 mixed4;
@@ -479,15 +473,19 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
         }
     }
 
-    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114): the relative-motion energy mu|v1 - v2|^2 is the Drude group's,
-    //      and leaves the atom group (see phase 1).  One pair per thread from the tile's dense pair list: a third of the
-    //      warp instructions of a phase that only the Drude particles' own lanes take part in. ------------------------
-    for (int j = tid; j < nPairs; j += CTHREADS) {
-        const uint32_t pw = pub.pairs[j];
-        const int loc = (int) (pw & 0xFFFFu), ploc = (int) (pw >> 16);
-        const mixed mass1 = pub.m[loc], mass2 = pub.m[ploc];
+    // ---- phase 3: Drude pairs (drudeNoseHoover.cu:99-114), the Drude thread owning the pair: the relative-motion energy
+    //      mu|v1 - v2|^2 is the Drude group's, and leaves the atom group (see phase 1) -------------------------------
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const uint32_t mw = meta[it];
+        if (!(mw & VVB200_META_NH) || ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) != VVB200_ROLE_DRUDE)
+            continue;
+        const int loc = it * CTHREADS + tid;
+        const int ploc = loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS;
+        const mixed4 v = vel[it];     // .w = mass
+        const mixed mass1 = v.w, mass2 = pub.m[ploc];
         const mixed redMass = mass1 * mass2 * rcpMass(mass1 + mass2);       // = 1 / ((m1+m2) w1 w2)
-        const mixed rx = pub.vx[loc] - pub.vx[ploc], ry = pub.vy[loc] - pub.vy[ploc], rz = pub.vz[loc] - pub.vz[ploc];
+        const mixed rx = v.x - pub.vx[ploc], ry = v.y - pub.vy[ploc], rz = v.z - pub.vz[ploc];
         const mixed e = (rx * rx + ry * ry + rz * rz) * redMass;
         acc[2] += e;
         acc[0] -= e;
@@ -745,14 +743,11 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
             const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
             const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
-            const int pcnt = p.kickOnly ? 0 : (d1.z + 3) & ~3;
             st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
-            st.desc[6] = p.kickOnly ? 0 : d1.z;
-            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u + pcnt * 4u;
+            uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u;
             if (KICK != KICK_NONE) bytes += 3u * cnt * 8u;
             if (EXTRA) bytes += cnt * (uint32_t) sizeof(real4);
             mbarArriveExpectTx(full + s, bytes);
-            if (pcnt) bulkLoad(st.pairs, p.tilePairs + d1.y, pcnt * 4u, full + s);
             bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
             if (KICK != KICK_NONE) {
                 bulkLoad(st.f[0], p.force + a0, cnt * 8u, full + s);
@@ -787,7 +782,6 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
         PublishedA<MODE, EXTRA> &pub = sm.pub[buf];
         const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
-        const int nPairs = st.desc[6];
         mixed4 vel[ITEMS];
         uint32_t meta[ITEMS];
         passAPhase1<MODE, KICK, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid);
@@ -798,7 +792,7 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
             continue;
         }
         consumerBarrier();
-        passAPhase23<MODE, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst, nPairs);
+        passAPhase23<MODE, EXTRA, false>(p, c, st, pub, vel, meta, acc, tid, t0, t1, m0, nMol, molFirst);
         buf ^= 1;
     }
 
@@ -840,7 +834,6 @@ template <int MODE> struct StageRed {
     typename Prec<MODE>::mixed4 velm[PADT];
     uint32_t meta[PADT];
     int32_t molInfo[MAXMOL + 8];
-    uint32_t pairs[MAXPAIRS + 4];
     int32_t desc[8];
 };
 struct ScratchRed {
@@ -894,10 +887,8 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
             const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
             const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
-            const int pcnt = (d1.z + 3) & ~3;
-            st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x; st.desc[6] = d1.z;
-            mbarArriveExpectTx(full + s, cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u + pcnt * 4u);
-            if (pcnt) bulkLoad(st.pairs, p.tilePairs + d1.y, pcnt * 4u, full + s);
+            st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
+            mbarArriveExpectTx(full + s, cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u);
             bulkLoad(st.velm, reinterpret_cast<const mixed4 *>(p.velm) + a0, cnt * (uint32_t) sizeof(mixed4), full + s);
             bulkLoad(st.meta, p.slotMeta + a0, cnt * 4u, full + s);
             if (mcnt) bulkLoad(st.molInfo, p.tileMolInfo + ma0, mcnt * 4u, full + s);
@@ -919,15 +910,26 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
         const int t0 = st.desc[0], t1 = st.desc[1], m0 = st.desc[2], nMol = useCOM ? st.desc[3] : 0, molFirst = st.desc[4];
         const int sl0 = t0 - (t0 & ~3), ml0 = m0 - (m0 & ~3);
         const mixed4 *sv = st.velm + sl0;      // (vx, vy, vz, 1/m) per tile-local slot
-        // ---- per particle: m|v|^2 of every massive thermostat particle (see passAPhase1) ----
+        // ---- per particle: m|v|^2 of every massive thermostat particle (see passAPhase1) and, on the Drude's lane, the
+        //      pair's relative-motion energy mu|v1 - v2|^2 (drudeNoseHoover.cu:99-114) ----
+        mixed pairRel[ITEMS];
 #pragma unroll
         for (int it = 0; it < ITEMS; it++) {
             const int loc = it * CTHREADS + tid;
+            pairRel[it] = 0;
             if (t0 + loc < t1) {
                 const mixed4 v = sv[loc];
                 const uint32_t mw = st.meta[sl0 + loc];
+                const mixed mass = v.w != 0 ? rcpMass(v.w) : (mixed) 0;
                 if ((mw & VVB200_META_NH) && v.w != 0)
-                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * rcpMass(v.w);
+                    acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * mass;
+                if ((mw & VVB200_META_NH) && ((mw >> VVB200_META_ROLE_SHIFT) & VVB200_META_ROLE_MASK) == VVB200_ROLE_DRUDE) {
+                    const mixed4 q = sv[loc + (int) (mw >> VVB200_META_PARTNER_SHIFT) - VVB200_META_PARTNER_BIAS];
+                    const mixed mass2 = rcpMass(q.w);
+                    const mixed redMass = mass * mass2 * rcpMass(mass + mass2);
+                    const mixed rx = v.x - q.x, ry = v.y - q.y, rz = v.z - q.z;
+                    pairRel[it] = (rx * rx + ry * ry + rz * rz) * redMass;
+                }
             }
         }
         // ---- molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), COM_LANES lanes per molecule ----
@@ -983,20 +985,14 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
                 }
             }
         }
-        // ---- Drude pairs (drudeNoseHoover.cu:99-114): mu|v1 - v2|^2, one pair of the tile's dense list per thread, after
-        //      the molecule terms -- the order and the thread pass A adds them in (bit-identical sums) ----
-        for (int j = tid; j < st.desc[6]; j += CTHREADS) {
-            const uint32_t pw = st.pairs[j];
-            const mixed4 v = sv[pw & 0xFFFFu], q = sv[pw >> 16];
-            const mixed mass1 = rcpMass(v.w), mass2 = rcpMass(q.w);
-            const mixed redMass = mass1 * mass2 * rcpMass(mass1 + mass2);
-            const mixed rx = v.x - q.x, ry = v.y - q.y, rz = v.z - q.z;
-            const mixed e = (rx * rx + ry * ry + rz * rz) * redMass;
-            acc[2] += e;
-            acc[0] -= e;
-        }
         mbarArrive(empty + s);      // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
+        // the pair terms join the sums AFTER the molecule terms: the order pass A adds them in (bit-identical sums)
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            acc[2] += pairRel[it];
+            acc[0] -= pairRel[it];
+        }
     }
 
     if (!blockReduceAndTicket<3>(p, sm, acc, tid))
@@ -1510,7 +1506,7 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
             mbarInit(full + s, 1);
             mbarInit(empty + s, CTHREADS_B);
         }
-        mbarInit(ready, 1);
+        mbarInit(ready, 4);      // the four lanes that poll the factor records
         fenceBarrierInit();
         expiredS = 0;
     }
@@ -1629,10 +1625,7 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
                 __nanosleep(20);
             }
             facS[tid] = v;
-        }
-        if (tid < 32) {
-            __syncwarp();
-            if (tid == 0) mbarArrive(ready);
+            mbarArrive(ready);      // each writer arrives for its own value (release)
         }
         mbarWait(ready, 0);
     }
