@@ -46,7 +46,7 @@ def main():
         mode = os.environ.get("VVB200_EXCHANGE", "auto")
         dp = vv.DistributedPlan(local_spec, params, "mixed").upload(peer={"auto": None, "nccl": False, "peer": True}[mode])
         if rank == 0:
-            print(f"[{name}] exchange: {'NVLink peer memory inside the NHC kernel' if dp.peer else 'NCCL all-reduce'}", flush=True)
+            print(f"[{name}] exchange: {'NVLink peer memory inside pass A's last block' if dp.peer else 'NCCL all-reduce'}", flush=True)
         bufs = vv.DeviceBuffers(lstate)
         for _ in range(steps):
             dp.step_middle(bufs, inv_box_z=inv_box_z)
@@ -73,7 +73,10 @@ def main():
         for _ in range(steps):
             dp2.step_host(hs, inv_box_z=inv_box_z)
         eh = max(rel_err(hs.velm[: b - a, :3], got.velm[: b - a, :3]), rel_err(hs.positions()[: b - a], got.positions()[: b - a]))
-        host_ok = eh < 1e-11
+        # the chunked pipeline adds its per-chunk sums up in another order than the resident step: scale factors differ in
+        # their last bits, the hard wall's r - maxDrudeDistance cancellation amplifies that (conftest: <= 6e-11 observed
+        # between code paths with the wall on) -- the bar is the one of the N-rank vs 1-rank comparison above
+        host_ok = eh < 1e-9
         ok = ok and host_ok
         if rank == 0:
             print(f"[{name}] host-buffer pipeline vs device-resident steps: {eh:.2e} -> {'OK' if host_ok else 'FAIL'}", flush=True)
