@@ -411,6 +411,35 @@ def small_system_leg(vv, torch, precision, n_ip=1250, steps=400, graph=True):
                     "blocking host round trip for the same step (profiles/configs_r02.json)"}
 
 
+def sweep_leg(vv, torch, precision, n_ip, peak, warmup=5, steps=20, repeats=5, long_steps=200):
+    """Whole-step time at another size under the HEADLINE's protocol: `steps` steps after `warmup` warm-up steps from the
+    Maxwell-Boltzmann start state (reloaded, thermostat chains zeroed, for each of `repeats` measurements; the median is
+    reported).  The protocol matters: frozen forces pump the Drude oscillators, so the hard wall -- the path's one
+    data-dependent branch -- fires more and more often over hundreds of steps (`us_per_step_after_200_steps` shows it);
+    a simulation with a force field stays at the start state's fire rate."""
+    spec = vv.make_bulk_ionic_liquid(n_ip)
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, precision, force_sigma=FORCE_SIGMA)
+    plan = vv.Plan(spec, params, precision).upload()
+    b = vv.DeviceBuffers(host)
+    times = []
+    l0 = plan.launch_count
+    for _ in range(repeats):
+        b.load(host)
+        reset_thermostat(plan)
+        times.append(time_calls(torch, lambda: plan.step_middle(b), steps, warmup=warmup))
+    launches = (plan.launch_count - l0) / (repeats * (steps + warmup))
+    us = float(np.median(times))
+    for _ in range(long_steps):
+        plan.step_middle(b)
+    late = time_calls(torch, lambda: plan.step_middle(b), steps, warmup=0)
+    gbs = (BYTES_PASS_A + BYTES_PASS_B) * spec.n / (us * 1e-6) / 1e9
+    return {"particles": spec.n, "us_per_step": us, "us_per_step_all_repeats": times, "launches_per_step": launches,
+            "step_gbs": gbs, "step_frac": gbs / peak,
+            "protocol": f"{steps} steps after {warmup} warm-up steps from the start state, median of {repeats} (the headline's protocol)",
+            "us_per_step_after_200_steps": late}
+
+
 def flows_leg(vv, torch, args, spec, params, plan, bufs, peak, steps):
     """The other flows of the path at the headline size (single-GPU runs), whole calls timed with CUDA events and no
     per-kernel events in between; `frac` = algorithmic bytes / time / measured copy peak."""
@@ -918,12 +947,7 @@ def main():
     #      the fraction of the HBM peak the 216 algorithmic bytes per particle amount to -------------------------
     sweep = None
     if rank == 0 and world == 1 and not args.no_sweep:
-        sweep = []
-        for n_ip in (27648, 110592):
-            r = small_system_leg(vv, torch, args.precision, n_ip=n_ip, steps=200, graph=False)
-            gbs = (BYTES_PASS_A + BYTES_PASS_B) * r["particles"] / (r["us_per_step"] * 1e-6) / 1e9
-            sweep.append({"particles": r["particles"], "us_per_step": r["us_per_step"], "launches_per_step": r["launches_per_step"],
-                          "step_gbs": gbs, "step_frac": gbs / peak})
+        sweep = [sweep_leg(vv, torch, args.precision, n_ip, peak, warmup=W, steps=K) for n_ip in (27648, 110592)]
 
     full_step = None
     if rank == 0 and world == 1 and not args.no_full_step:

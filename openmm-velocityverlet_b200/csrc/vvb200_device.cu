@@ -118,6 +118,12 @@ struct NhcDevice {
     double red[VVB200_NRED];     // this rank's (or, after an all-reduce, the global) sums
     double vBias;
     double invMassTotal;
+    // the part of the NEXT chain update that does not depend on the next kinetic energy (nhcPre), run at the end of the
+    // previous one: etaDot[k >= 1] after the first sweep and the exponential that multiplies etaDot[0]; valid for the step
+    // size preDt only (0 = not valid: the state was set from the host, or advanced by the unsplit routine)
+    double preEtaDot[3][VVB200_MAX_CHAINS + 1];
+    double preE0[3];
+    double preDt;
     int numTG, nc, loops;
 };
 
@@ -329,8 +335,10 @@ __device__ void nhcFinish(NhcDevice *s, double dt, int g, const double *red = nu
     }
     s->ke2[g] = ke2;
     s->vscale[g] = scale;
-    if (g == 0)
+    if (g == 0) {
         s->vBias = V;
+        s->preDt = 0.0;      // the unsplit routine does not look ahead
+    }
 }
 
 // ---- the chain update cut where the scale factor is known ---------------------------------------------------------
@@ -338,35 +346,38 @@ __device__ void nhcFinish(NhcDevice *s, double dt, int g, const double *red = nu
 // kinetic energy in exactly one place before the factor is final: etaDotDot[0].  Everything above it in the first sweep
 // (the chains ich = nc-1 .. 1 and the exponential that multiplies etaDot[0]) depends on the previous step only, and
 // everything after `factor` only prepares the next step.  So the block that finishes the reduction runs
-//     nhcPre   at kernel start, while the first tiles are still in flight (every block: any of them may arrive last)
 //     nhcCrit  ke2 -> etaDotDot[0] -> etaDot[0] -> factor = exp(-dt/2 etaDot[0]): one division and ONE exp on the
 //              critical path instead of six dependent exps and four divisions; the factor is published right away
-//     nhcPost  eta, the second sweep, the state for the next step -- off the critical path
+//     nhcPost  eta, the second sweep, the state for the next step -- and then nhcPre for the NEXT step, whose results
+//              (preEtaDot, preE0) travel in the thermostat state: all of it off the critical path
 // The operations, their operands and their order are those of nhcPropagateT (bit-identical results); other loop counts
-// and groups without a thermostat mass keep the unsplit routine inside nhcCrit.
+// and groups without a thermostat mass keep the unsplit routine inside nhcCrit.  preDt says which step size the
+// look-ahead is valid for; anything that sets the state from outside zeroes it and nhcCrit then runs nhcPre itself.
 __device__ __forceinline__ bool nhcSplittable(const NhcDevice *s, int g) {
     return s->loops == 1 && g < s->numTG && s->etaMass[g][0] > 0;
 }
 
-__device__ __noinline__ double nhcPre(NhcDevice *s, int g, double dt) {
+__device__ __noinline__ void nhcPre(NhcDevice *s, int g, double dt) {
     if (!nhcSplittable(s, g))
-        return 0.0;
+        return;
     const int nc = s->nc;
     const double h2 = dt / s->loops / 2, h4 = h2 / 2, h8 = h4 / 2;
+    double next = s->etaDot[g][nc];           // etaDot[k + 1] as the sweep sees it
     for (int k = nc - 1; k >= 1; k--) {
-        const double e = exp(-h8 * s->etaDot[g][k + 1]);
+        const double e = exp(-h8 * next);
         double x = s->etaDot[g][k];
         x *= e;
         x += s->etaDotDot[g][k] * h4;
         x *= e;
-        s->etaDot[g][k] = x;
+        s->preEtaDot[g][k] = x;
+        next = x;
     }
-    return exp(-h8 * s->etaDot[g][1]);
+    s->preE0[g] = exp(-h8 * next);
 }
 
-// threads 0..2 of the block that holds the final sums; returns nothing: ke2 / vscale / vBias land in *s
+// threads 0..2 of the block that holds the final sums; ke2 / vscale / vBias land in *s
 template <bool COS>
-__device__ __noinline__ void nhcCrit(NhcDevice *s, double dt, int g, const double *red, double e0) {
+__device__ __noinline__ void nhcCrit(NhcDevice *s, double dt, int g, const double *red) {
     double V = 0.0;
     if (COS)
         V = red[3] * s->invMassTotal;
@@ -376,6 +387,11 @@ __device__ __noinline__ void nhcCrit(NhcDevice *s, double dt, int g, const doubl
     double scale = 1.0;
     if (g < s->numTG) {
         if (nhcSplittable(s, g)) {
+            if (s->preDt != dt)
+                nhcPre(s, g, dt);       // no valid look-ahead (first step, state set from the host, step size changed)
+            for (int k = 1; k < s->nc; k++)
+                s->etaDot[g][k] = s->preEtaDot[g][k];
+            const double e0 = s->preE0[g];
             const double h2 = dt / s->loops / 2, h4 = h2 / 2;
             const double dd = (ke2 - s->NkbT[g]) / s->etaMass[g][0];
             double x = s->etaDot[g][0];
@@ -397,13 +413,16 @@ __device__ __noinline__ void nhcCrit(NhcDevice *s, double dt, int g, const doubl
         s->vBias = V;
 }
 
-__device__ __noinline__ void nhcPost(NhcDevice *s, double dt, int g, double e0) {
-    if (!nhcSplittable(s, g))
+// after nhcCrit, by the same three threads; `s` must not be read by anybody else until they are done
+__device__ __noinline__ void nhcPost(NhcDevice *s, double dt, int g) {
+    if (!nhcSplittable(s, g)) {
+        if (g == 0) s->preDt = 0.0;
         return;
+    }
     const int nc = s->nc;
     const double h2 = dt / s->loops / 2, h4 = h2 / 2, h8 = h4 / 2;
     const double kT = BOLTZ_D * s->tTarget[g];
-    const double ke2 = s->ke2[g], factor = s->vscale[g];
+    const double ke2 = s->ke2[g], factor = s->vscale[g], e0 = s->preE0[g];
     for (int k = 0; k < nc; k++)
         s->eta[g][k] += h2 * s->etaDot[g][k];
     const double dd = (ke2 * factor * factor - s->NkbT[g]) / s->etaMass[g][0];
@@ -423,6 +442,8 @@ __device__ __noinline__ void nhcPost(NhcDevice *s, double dt, int g, double e0) 
         y *= e;
         s->etaDot[g][k] = y;
     }
+    nhcPre(s, g, dt);               // the look-ahead for the next step
+    if (g == 0) s->preDt = dt;      // (every group of a plan is splittable or none is: loops is shared)
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
@@ -2192,6 +2213,7 @@ extern "C" int vvb200_set_thermostat_state(vvb200_plan *p, const vvb200_thermost
         for (int k = 0; k < nc + 1; k++)
             h.etaDot[g][k] = in->eta_dot[g * (nc + 1) + k];
     }
+    h.preDt = 0.0;       // the look-ahead of the chain update belongs to the old state
     CUDA_TRY(cudaMemcpyAsync(p->dev->nhc, &h, sizeof h, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return VVB200_OK;

@@ -452,6 +452,8 @@ static bool buildTiles(vvb200_plan *p) {
             const int perBlock = (N + 2 * p->tileSM - 1) / (2 * p->tileSM);
             cap = std::min(VVB200_TILE_CAP, std::max(128, (perBlock + 31) / 32 * 32));
         }
+        if (const char *t = getenv("VVB200_TILE_PARTICLES"))       // tuning: a fixed tile size
+            if (atoi(t) >= 64) cap = std::min(VVB200_TILE_CAP, atoi(t) / 32 * 32);
     }
     // Experiment kept behind VVB200_BALANCED_TILES=1 (off): the persistent grids of pass A (3 x 148 blocks) and pass B
     // (2 x 148) assign tiles round-robin, so mid-size systems leave part of the machine idle for a tile at the end
@@ -483,7 +485,7 @@ static bool buildTiles(vvb200_plan *p) {
         }
         // small tiles only pay while every tile still gets its own co-resident block (units that may not be split
         // leave tiles partly empty, so the count can exceed N / cap): otherwise grow the tile and cut again
-        if (ok && cap < VVB200_TILE_CAP && (int) p->tileStart.size() - 1 > 2 * p->tileSM) {
+        if (ok && cap < VVB200_TILE_CAP && (int) p->tileStart.size() - 1 > 2 * p->tileSM && !getenv("VVB200_TILE_PARTICLES")) {
             cap += 32;
             continue;
         }

@@ -9,9 +9,13 @@
 //   load tiles (cp.async.bulk, all issued up front)            velm, force, posq, posqCorrection, slot words
 //   pass A per tile (passAPhase1/23 of vvb200_stream.cuh)      kicked velocities written back INTO the stage,
 //                                                             molecular velocities into the stage's comV
-//   per-block partial sums -> arrival ticket -> grid barrier   the last block to arrive sums the partials, advances
-//                                                             the NH chains and releases a generation word the
-//                                                             other blocks wait on (ld.acquire.gpu, bounded)
+//   per-block partial sums -> arrival ticket -> grid barrier   the last block to arrive sums the partials, runs the part
+//                                                             of the chain update that yields the scale factors
+//                                                             (nhcCrit) and publishes them as self-validating records
+//                                                             tagged with this launch's generation; every block polls
+//                                                             the records (bounded).  The rest of the chain update runs
+//                                                             in the last block WHILE it does its pass B, on a warp that
+//                                                             holds no particles (tiles of <= 224 slots), else after it
 //   pass B per tile (passBTile) straight from the stage        one write of velm / posq / posqCorrection
 //
 // => 1 launch instead of 2, 156 instead of 224 B/particle (mixed), no HBM round trip of the kicked velocities.
@@ -53,7 +57,8 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
     typedef StageR<MODE, KICK, VARIANT, EXTRA> Stage;
     typedef ScratchA<MODE, EXTRA> Scratch;
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    __shared__ unsigned int expiredS;
+    __shared__ unsigned int expiredS, genS, helperS, lastS;
+    __shared__ double facS[4];
     __shared__ NhcDevice nhcS;      // every block prefetches the thermostat state: any of them may arrive last
     const int T = p.tilesPerBlock;
     constexpr size_t stageBytes = roundUp128(sizeof(Stage));
@@ -73,6 +78,9 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
         for (int j = 0; j < T; j++) mbarInit(full + j, 1);
         fenceBarrierInit();
         expiredS = 0;
+        genS = gen0;
+        lastS = 0;
+        int widest = 0;
         // ---- every tile of this block is requested up front; nothing is ever refilled ----
         for (int j = 0; j < T; j++) {
             const int tile = blockIdx.x + j * gridDim.x;
@@ -85,6 +93,7 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * j);
             const int a0 = d0.x & ~3, cnt = ((d0.y + 3) & ~3) - a0;
             const int ma0 = d0.z & ~3, mcnt = useCOM && d0.w > 0 ? ((d0.z + d0.w + 3) & ~3) - ma0 : 0;
+            widest = max(widest, d0.y - d0.x);
             st.desc[0] = d0.x; st.desc[1] = d0.y; st.desc[2] = d0.z; st.desc[3] = d0.w; st.desc[4] = d1.x;
             st.desc[5] = 0;                     // st.cbar is indexed by the tile-local molecule id
             uint32_t bytes = cnt * (uint32_t) (sizeof(mixed4) + sizeof(uint32_t)) + mcnt * 4u;
@@ -103,6 +112,9 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
             if (Stage::POSQ) bulkLoad(st.posq, reinterpret_cast<const real4 *>(p.posq) + a0, cnt * (uint32_t) sizeof(real4), full + j);
             if (Stage::CORR) bulkLoad(st.corr, reinterpret_cast<const real4 *>(p.corr) + a0, cnt * (uint32_t) sizeof(real4), full + j);
         }
+        // the last warp holds no particle of pass B when no tile of this block is wider than CTHREADS - 32 slots (the
+        // tiles of the systems this kernel is for are 128-224 slots): it is free for the rest of the chain update
+        helperS = widest <= CTHREADS - 32 ? 1u : 0u;
     }
     if (p.doReduce)
         nhcFetch(&nhcS, p.nhc, tid, 32);
@@ -134,32 +146,48 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
         }
     }
 
-    // ===== grid barrier: partial sums -> last block: totals + NH chains -> everyone goes on =====
+    // ===== grid barrier: partial sums -> last block: totals + scale factors -> everyone goes on =====
     traceMark(3);
+    constexpr int HELPER0 = CTHREADS - 32;      // first thread of the helper warp
     if (p.doReduce) {
         const bool last = blockReduceAndTicket<NR>(p, sm, acc, tid);
         traceMark(4);
+        const unsigned long long tag = (unsigned long long) genS + 2ull;      // >= 2: the streaming kernels use 0 and 1
         if (last) {
-            // (the chain update is not split here: the last block has tiles of its own to finish, so what it does after
-            // the release is on the launch's critical path either way)
-            lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS);
-            consumerBarrier();
-            nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
-            consumerBarrier();        // the release below is cumulative over what the barrier ordered before it
-            if (tid == 0) st_release_gpu(p.gridGen, gen0 + 1u);
+            // the three chain threads sit in the helper warp when there is one: after nhcCrit they go straight on to the
+            // rest of the chain update while the other seven warps do pass B
+            if (tid == 0) lastS = 1;
+            lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS, p.fuseNHC != 0, helperS ? HELPER0 : 0, tag, true, true);
+        }
+        // every block, the last one included, takes the factors from the records (value + tag in one 128-bit word)
+        if (p.fuseNHC) {
+            if (tid < 4) {
+                double v = 0;
+                const long long c0 = clock64();
+                while (!factorPoll(p.factorRec + tid, tag, &v)) {
+                    if (clock64() - c0 > 2000000000LL) {   // ~1 s: blocks were not co-resident; poison, do not hang
+                        expiredS = 1;
+                        break;
+                    }
+                    __nanosleep(20);
+                }
+                if (p.numSplit != 0) __threadfence();      // acquire side of the cut molecules' velocities
+                facS[tid] = v;
+            }
+        } else if (last) {
+            __threadfence();
+            if (tid == 0) st_release_gpu(p.gridGen, genS + 1u);
         } else if (tid == 0) {
             const long long c0 = clock64();
-            while (ld_acquire_gpu(p.gridGen) == gen0) {
-                if (clock64() - c0 > 2000000000LL) {   // ~1 s: blocks were not co-resident; poison, do not hang
-                    expiredS = 1;
-                    break;
-                }
+            while (ld_acquire_gpu(p.gridGen) == genS) {
+                if (clock64() - c0 > 2000000000LL) { expiredS = 1; break; }
                 __nanosleep(32);
             }
         }
     }
     __syncthreads();
     traceMark(5);
+    const bool helperBusy = p.doReduce && p.fuseNHC && lastS && helperS && tid >= HELPER0;   // this warp: chain update, not pass B
 
     // molecules cut across tiles were finished by the last block: fetch their velocities into the stages
     if (p.numSplit > 0 && useCOM) {
@@ -182,18 +210,35 @@ __global__ void __launch_bounds__(CTHREADS, RESIDENT_MINBLOCKS) resident_step_ke
     }
 
     // ===== pass B from the same stages =====
-    BCtx<MODE> cb = makeBCtx<MODE>(p, EXTRA);
+    BCtx<MODE> cb = makeBCtx<MODE>(p, EXTRA, p.doReduce && p.fuseNHC ? facS : nullptr);
     cb.writeAllVel = KICK != KICK_NONE;
     if (expiredS) {
         const mixed nan = (mixed) __longlong_as_double(0x7ff8000000000000LL);
         cb.sA = cb.sC = cb.sD = nan;
     }
-    for (int j = 0; j < T; j++) {
-        const int tile = blockIdx.x + j * gridDim.x;
-        if (tile >= p.numTiles) break;
-        mbarWait(full + j, 0);
-        Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * j);
-        passBTile<MODE, VARIANT, EXTRA, CTHREADS>(p, cb, st, tid);
+    if (helperBusy) {
+        // the last block's helper warp: the second sweep of the chain update, the look-ahead for the next step, the state
+        // back to global memory and the generation word -- concurrently with the other warps' pass B
+        if (tid - HELPER0 < 3) nhcPost(&nhcS, p.dt, tid - HELPER0);
+        __syncwarp();
+        for (int i = tid - HELPER0; i < (int) (sizeof(NhcDevice) / 8); i += 32)
+            reinterpret_cast<double *>(p.nhc)[i] = reinterpret_cast<const double *>(&nhcS)[i];
+        if (tid == HELPER0) *p.gridGen = genS + 1u;      // read again only by the next launch
+    } else {
+        for (int j = 0; j < T; j++) {
+            const int tile = blockIdx.x + j * gridDim.x;
+            if (tile >= p.numTiles) break;
+            mbarWait(full + j, 0);
+            Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * j);
+            passBTile<MODE, VARIANT, EXTRA, CTHREADS>(p, cb, st, tid);
+        }
     }
     traceMark(6);
+    if (p.doReduce && p.fuseNHC && lastS && !helperS) {
+        // no free warp (tiles wider than 224 slots): the rest of the chain update after this block's pass B
+        if (tid < 3) nhcPost(&nhcS, p.dt, tid);
+        __syncthreads();
+        nhcStore(p.nhc, &nhcS, tid);
+        if (tid == 0) *p.gridGen = genS + 1u;
+    }
 }

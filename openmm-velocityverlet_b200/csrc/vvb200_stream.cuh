@@ -163,7 +163,6 @@ template <int MODE, bool EXTRA> struct ScratchA {
     typedef typename Prec<MODE>::mixed mixed;
     PublishedA<MODE, EXTRA> pub[2];
     double red[CTHREADS / 32][VVB200_NRED];
-    double nhcE0[4];                 // nhcPre's exponential per temperature group
     unsigned long long peerSeq;
     unsigned int ticket;
 };
@@ -498,30 +497,18 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
     }
 }
 
-// NhcDevice <-> shared-memory copy by threads first .. first + sizeof/8 - 1 (plain 8-byte words; __ldcg: the source may
+// NhcDevice <-> shared-memory copy by threads first .. CTHREADS - 1 (plain 8-byte words; __ldcg: the source may
 // have been written by another SM earlier in this launch sequence)
-static_assert(sizeof(NhcDevice) % 8 == 0 && sizeof(NhcDevice) / 8 <= CTHREADS - 32, "NhcDevice copy");
+static_assert(sizeof(NhcDevice) % 8 == 0, "NhcDevice copy");
 __device__ __forceinline__ void nhcFetch(NhcDevice *shared, const NhcDevice *global, const int tid, const int first) {
-    const int i = tid - first;
-    if (i >= 0 && i < (int) (sizeof(NhcDevice) / 8))
-        reinterpret_cast<double *>(shared)[i] = __ldcg(reinterpret_cast<const double *>(global) + i);
-}
-// the same by ONE warp (threads first .. first + 31), which then runs the part of the chain update that does not depend
-// on this step's kinetic energy (nhcPre, device.cu) while the block's first tiles are still in flight
-__device__ __forceinline__ void nhcFetchAndPre(NhcDevice *shared, const NhcDevice *global, double *e0, const double dt,
-                                               const int tid, const int first) {
-    const int lane = tid - first;
-    if (lane < 0 || lane >= 32)
+    if (tid < first)
         return;
-    for (int i = lane; i < (int) (sizeof(NhcDevice) / 8); i += 32)
+    for (int i = tid - first; i < (int) (sizeof(NhcDevice) / 8); i += CTHREADS - first)
         reinterpret_cast<double *>(shared)[i] = __ldcg(reinterpret_cast<const double *>(global) + i);
-    __syncwarp();
-    if (lane < 3)
-        e0[lane] = nhcPre(shared, lane, dt);
 }
 __device__ __forceinline__ void nhcStore(NhcDevice *global, const NhcDevice *shared, const int tid) {
-    if (tid < (int) (sizeof(NhcDevice) / 8))
-        reinterpret_cast<double *>(global)[tid] = reinterpret_cast<const double *>(shared)[tid];
+    for (int i = tid; i < (int) (sizeof(NhcDevice) / 8); i += CTHREADS)
+        reinterpret_cast<double *>(global)[i] = reinterpret_cast<const double *>(shared)[i];
 }
 
 // ---- per-block reduction of the thread accumulators (fixed order) and the arrival ticket: true for the block
@@ -559,8 +546,11 @@ __device__ __forceinline__ bool blockReduceAndTicket(const KParams &p, Scratch &
 // back afterwards (resident kernel: saves the chain's serial L2 round trips).
 template <int MODE, int NR, class Scratch>
 __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, const bool cosine, const int tid,
-                                                NhcDevice *work = nullptr, const bool splitChain = false) {
-    // splitChain: the caller ran nhcPre on `work` (nhcFetchAndPre) -- the chain update goes on from there
+                                                NhcDevice *work = nullptr, const bool splitChain = false,
+                                                const int chainBase = 0, const unsigned long long tag = 1ull,
+                                                const bool publish = false, const bool deferPost = false) {
+    // splitChain: the chain update is cut at the scale factor (nhcCrit / nhcPost); threads chainBase .. chainBase + 2 run
+    // it; publish: each factor leaves as a FactorRec with `tag` the moment it exists; deferPost: the caller runs nhcPost
     typedef typename Prec<MODE>::mixed mixed;
     typedef typename Prec<MODE>::mixed4 mixed4;
     if (!work) work = p.nhc;
@@ -676,22 +666,23 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
     traceMark(7);
     if (tid == 0) traceMarkS(0, 7);
 #endif
-    if (p.fuseNHC && tid < 3) {
+    const int g = tid - chainBase;
+    if (p.fuseNHC && g >= 0 && g < 3) {
         if (!splitChain) {
-            if (cosine) nhcFinish<true>(work, p.dt, tid, sm.red[0]);
-            else nhcFinish<false>(work, p.dt, tid, sm.red[0]);
+            if (cosine) nhcFinish<true>(work, p.dt, g, sm.red[0]);
+            else nhcFinish<false>(work, p.dt, g, sm.red[0]);
         } else {
-            const double e0 = sm.nhcE0[tid];
-            if (cosine) nhcCrit<true>(work, p.dt, tid, sm.red[0], e0);
-            else nhcCrit<false>(work, p.dt, tid, sm.red[0], e0);
+            if (cosine) nhcCrit<true>(work, p.dt, g, sm.red[0]);
+            else nhcCrit<false>(work, p.dt, g, sm.red[0]);
             // what pass B needs leaves right now, each factor in a self-validating record (no fence, no second word);
             // the state itself follows with nhcStore once the rest of the chain update is done
-            if (p.flagSync) {
-                factorPublish(p.factorRec + tid, work->vscale[tid], 1ull);
-                if (tid == 0) factorPublish(p.factorRec + 3, work->vBias, 1ull);
+            if (publish) {
+                if (p.numSplit != 0) __threadfence();      // the cut molecules' velocities (ordered by the barriers above) first
+                factorPublish(p.factorRec + g, work->vscale[g], tag);
+                if (g == 0) factorPublish(p.factorRec + 3, work->vBias, tag);
             }
-            if (tid == 0) traceMarkS(0, 5);
-            nhcPost(work, p.dt, tid, e0);
+            if (g == 0) traceMarkS(0, 5);
+            if (!deferPost) nhcPost(work, p.dt, g);
         }
     }
 }
@@ -766,7 +757,7 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
     // every block prefetches the thermostat state (any of them may arrive last): the chains then run on shared memory
     // instead of a string of dependent L2 round trips
     if (p.fuseNHC)
-        nhcFetchAndPre(&nhcS, p.nhc, sm.nhcE0, p.dt, tid, 0);
+        nhcFetch(&nhcS, p.nhc, tid, 0);
     const ACtx<MODE> c = makeACtx<MODE, KICK>(p, EXTRA);
     constexpr int NR = EXTRA ? VVB200_NRED : 3;
     // per-thread accumulators in `mixed` like the reference's kineticEnergyBuffer
@@ -803,7 +794,7 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
     }
     if (tid == 0) traceMarkS(0, 4);
     if (p.fuseNHC) {
-        lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS, true);
+        lastBlockFinish<MODE, NR>(p, sm, cosine, tid, &nhcS, true, 0, 1ull, p.flagSync != 0);
         consumerBarrier();
         nhcStore(p.nhc, &nhcS, tid);      // the advanced state back to global memory
         if (tid == 0) traceMarkS(0, 6);
@@ -838,7 +829,6 @@ template <int MODE> struct StageRed {
 };
 struct ScratchRed {
     double red[CTHREADS / 32][VVB200_NRED];
-    double nhcE0[4];
     unsigned long long peerSeq;
     unsigned int ticket;
 };
@@ -899,7 +889,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
 
     // ===== consumers =====
     if (p.fuseNHC)
-        nhcFetchAndPre(&nhcS, p.nhc, sm.nhcE0, p.dt, tid, 0);
+        nhcFetch(&nhcS, p.nhc, tid, 0);
     mixed acc[3] = {0, 0, 0};
     mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
     int s = 0;
@@ -998,7 +988,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
     if (!blockReduceAndTicket<3>(p, sm, acc, tid))
         return;
     if (p.fuseNHC) {
-        lastBlockFinish<MODE, 3>(p, sm, false, tid, &nhcS, true);
+        lastBlockFinish<MODE, 3>(p, sm, false, tid, &nhcS, true, 0, 1ull, p.flagSync != 0);
         consumerBarrier();
         nhcStore(p.nhc, &nhcS, tid);
     } else {
