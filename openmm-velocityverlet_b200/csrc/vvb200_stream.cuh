@@ -682,7 +682,10 @@ __device__ __forceinline__ void lastBlockFinish(const KParams &p, Scratch &sm, c
                 if (g == 0) factorPublish(p.factorRec + 3, work->vBias, tag);
             }
             if (g == 0) traceMarkS(0, 5);
-            if (!deferPost) nhcPost(work, p.dt, g);
+            if (!deferPost) {
+                __syncwarp(0x7u);      // nhcPost rewrites preDt, which the other two read in nhcCrit (chainBase is a warp's first thread)
+                nhcPost(work, p.dt, g);
+            }
         }
     }
 }
