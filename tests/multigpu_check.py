@@ -46,7 +46,7 @@ def main():
         mode = os.environ.get("VVB200_EXCHANGE", "auto")
         dp = vv.DistributedPlan(local_spec, params, "mixed").upload(peer={"auto": None, "nccl": False, "peer": True}[mode])
         if rank == 0:
-            print(f"[{name}] exchange: {'NVLink peer memory inside pass A's last block' if dp.peer else 'NCCL all-reduce'}", flush=True)
+            print(f"[{name}] exchange: {'NVLink peer memory inside the last block of pass A' if dp.peer else 'NCCL all-reduce'}", flush=True)
         bufs = vv.DeviceBuffers(lstate)
         for _ in range(steps):
             dp.step_middle(bufs, inv_box_z=inv_box_z)

@@ -70,3 +70,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "vvoracle" not in text and "vv_oracle" not in text and "oracle/" not in text, f
+
+
+def test_every_script_compiles():
+    """scripts that only ever run on the GPU box (multi-rank checks, diagnostics, tools, the benches) must at least be
+    valid Python here: a syntax error in tests/multigpu_check.py would otherwise first show up on an 8-GPU box"""
+    import glob
+    import py_compile
+    files = [f for pat in ("tests/*.py", "tools/*.py", "*.py", "openmm-velocityverlet_b200/*.py", "oracle/*.py", "profiles/*.py")
+             for f in glob.glob(os.path.join(ROOT, pat))]
+    assert len(files) > 30
+    for f in files:
+        py_compile.compile(f, doraise=True)
