@@ -300,6 +300,15 @@ int vvb200_measure_temperatures(vvb200_plan *plan, const vvb200_buffers *buf, co
 int vvb200_set_resident_mode(vvb200_plan *plan, int mode);
 int64_t vvb200_resident_launch_count(const vvb200_plan *plan);
 
+/* Launch behaviour fixed per plan at vvb200_plan_upload (environment, for tests and tuning; defaults are what ships):
+ *   VVB200_PDL=0        no programmatic dependent launch between the two streaming passes
+ *   VVB200_HANDOVER=0   pass B waits for the whole of pass A (griddepcontrol.wait) instead of taking over through the
+ *                       hand-over word and the factor records its last block publishes (vvb200_stream.cuh); applies to the
+ *                       calls that launch both passes: vvb200_step_middle, vvb200_thermostat,
+ *                       vvb200_middle_thermostat_delta, vvb200_step_vv_first / _second
+ *   VVB200_B_REVERSE=0  under the hand-over pass B draws its tiles first-to-last instead of last-to-first
+ * Results are bitwise identical in every combination (tests/test_gpu_edge_cases.py). */
+
 /* Optional per-kernel timing for bench.py's roofline: CUDA events are recorded on the launching stream
  * around the pass-A kernel (kick and / or reductions) and the pass-B kernel (scale / drift / position
  * write) of every step-like call -- vvb200_step_middle, vvb200_step_vv_first / _second, and the split
