@@ -408,6 +408,8 @@ __device__ __forceinline__ void passAPhase23(const KParams &p, const ACtx<MODE> 
     if (nMol > 0) {
         const int grp = tid / COM_LANES, sub = tid % COM_LANES;
         for (int jb = 0; jb < nMol; jb += CTHREADS / COM_LANES) {
+            if (jb + (tid & ~31) / COM_LANES >= nMol)
+                break;      // warp-uniform: no lane of this warp holds a molecule, in this round or any later one
             const int j = jb + grp;
             const bool active = j < nMol;
             mixed sx = 0, sy = 0, sz = 0, sc = 0, comMass = 0;
@@ -791,6 +793,8 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
     }
 
     if (tid == 0) traceMarkS(0, 3);
+    if (p.kickOnly)
+        return;         // nothing was reduced (vvb200_middle_kick, any-topology kick): no partials, no ticket, no last block
     if (!blockReduceAndTicket<NR>(p, sm, acc, tid)) {
         if (tid == 0) traceMarkS(0, 4);
         return;
@@ -838,9 +842,13 @@ struct ScratchRed {
 template <int MODE> constexpr size_t smemBytesRed(int stages) {
     return roundUp128(sizeof(StageRed<MODE>)) * stages + roundUp128(sizeof(ScratchRed)) + 16 * stages + 128;
 }
-#ifndef MINBLOCKS_RED
-#define MINBLOCKS_RED 4       // 56 registers: warps are independent here (no block barrier), a fourth block is worth 3 %
+#ifndef ROT_RED
+#define ROT_RED (CTHREADS / 2)      // rotation of the molecule lanes from one tile of a block to the next (0: none)
 #endif
+#ifndef MINBLOCKS_RED
+#define MINBLOCKS_RED 3       // 3 blocks x 3 stages, no spills: with the rotated molecule lanes the deeper ring (the warps
+#endif                        // slip further against each other) is worth more than a fourth block -- 137 -> 128 us
+
 
 template <int MODE>
 __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const KParams p) {
@@ -895,7 +903,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
         nhcFetch(&nhcS, p.nhc, tid, 0);
     mixed acc[3] = {0, 0, 0};
     mixed4 *comV = reinterpret_cast<mixed4 *>(p.comV);
-    int s = 0;
+    int s = 0, rot = 0;
     uint32_t phase = 0;
     for (int tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
         mbarWait(full + s, phase);
@@ -926,9 +934,19 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
             }
         }
         // ---- molecular centre-of-mass velocities (drudeNoseHoover.cu:11-30), COM_LANES lanes per molecule ----
+        // A tile of the ionic-liquid box holds ~27 molecules: 108 of the 256 threads, i.e. the block's first warps, carry
+        // the whole molecule phase (~280 instructions a tile against ~140 for the particle phase) while the others run
+        // ahead by what the ring allows and then spin on a `full` barrier.  No barrier separates the tiles here, so the
+        // molecule lanes ROTATE by half a block with every tile a block takes and each warp is the heavy one every other
+        // tile.  (The block's first tile is unrotated: a system of one tile per block -- every bitwise fused-vs-split
+        // test -- sums in pass A's thread order; with several tiles per block the two kernels' per-block sums group the
+        // tiles differently anyway: 444 vs 444-592 blocks.)
         if (nMol > 0) {
-            const int grp = tid / COM_LANES, sub = tid % COM_LANES;
+            const int rtid = (tid + rot) & (CTHREADS - 1);
+            const int grp = rtid / COM_LANES, sub = rtid % COM_LANES;
             for (int jb = 0; jb < nMol; jb += CTHREADS / COM_LANES) {
+                if (jb + (rtid & ~31) / COM_LANES >= nMol)
+                    break;      // warp-uniform (see passAPhase23): the warps behind the tile's last molecule go on
                 const int j = jb + grp;
                 const bool active = j < nMol;
                 mixed sx = 0, sy = 0, sz = 0, comMass = 0;
@@ -980,6 +998,7 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
         }
         mbarArrive(empty + s);      // this thread is done reading the stage
         if (++s == stages) { s = 0; phase ^= 1; }
+        rot ^= ROT_RED;
         // the pair terms join the sums AFTER the molecule terms: the order pass A adds them in (bit-identical sums)
 #pragma unroll
         for (int it = 0; it < ITEMS; it++) {
