@@ -306,6 +306,31 @@ def test_large_system_properties(vv, vo):
     assert rel_err(got.velm[: spec.n, :3], want.velm[: spec.n, :3]) <= 1e-6
 
 
+def test_reduce_only_pass_with_several_tiles_per_block(vv, vo):
+    """1M particles are 2,000 tiles on at most 444 blocks: every block of the reduce-only pass takes several tiles and its
+    molecule lanes rotate from one tile to the next (vvb200_stream.cuh, reduce_kernel).  Its group energies against the
+    oracle's and against pass A's sums of the same velocities (zero forces: the kick adds exact zeros)."""
+    spec = vv.make_bulk_ionic_liquid(27648)          # 1,022,976 particles
+    params = vv.Params(max_drude_distance=0.02).resolved_for(spec)
+    host = vv.make_state(spec, "mixed", force_sigma=0.0)
+    red = vv.Plan(spec, params, "mixed").upload()
+    b1 = vv.DeviceBuffers(host)
+    red.thermostat(b1)
+    ke_red = red.thermostat_state()["ke2"]
+    fused = vv.Plan(spec, params, "mixed").upload()
+    b2 = vv.DeviceBuffers(host)
+    fused.step_middle(b2)
+    ke_a = fused.thermostat_state()["ke2"]
+    oracle = vo.Oracle(spec, params, "mixed", literal=False, threads=0)
+    want = host.copy()
+    oracle.scale_velocity(want)
+    ke_o = oracle.thermostat_state()["ke2"]
+    assert rel_err(ke_red, ke_a) <= 1e-13 and rel_err(ke_red, ke_o[: len(ke_red)]) <= TOL_KE["mixed"]
+    assert rel_err(red.thermostat_state()["vscale"], fused.thermostat_state()["vscale"]) <= 1e-13
+    # the molecular velocities both passes leave behind
+    assert rel_err(red.com_velocities(), fused.com_velocities()) <= 1e-13
+
+
 def test_vv_split_entry_points_match_fused(vv, vo):
     """velocity-Verlet scheme through the VVKernels.h-shaped calls (thermostat / half kick + posDelta / positions /
     half kick / thermostat, as the OpenMM glue issues them around constraints) == the fused vv_first + vv_second"""
