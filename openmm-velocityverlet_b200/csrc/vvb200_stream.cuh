@@ -816,17 +816,20 @@ __global__ void __launch_bounds__(BTHREADS, passABlocks(KICK)) kick_reduce_kerne
 // What the thermostat needs when the kick is not part of the same call: the constraint-bearing flow (OpenMM's velocity
 // constraints run between the kick and the thermostat, CudaVVKernels.cpp:151), the velocity-Verlet scheme's leading half
 // step, vvb200_thermostat, vvb200_measure_temperatures.  36 B/particle (velm + slot word), nothing to write but comV.
-// kick_reduce_kernel<KICK_NONE> ran it at 0.39 of the copy roofline, and ncu says why (profiles/ncu_r02_reduce_summary.txt):
-// the SHARED-MEMORY pipe is saturated (l1tex lsu wavefronts 82 % of peak, 40 % of them bank conflicts), then the issue
-// slots (a conflict-free variant with per-lane selects ran 175M warp instructions at 66 % issue utilisation) -- not DRAM
-// (38 %), not fp64 (31 %); a deeper ring or a fourth block changes nothing.  This kernel does the same arithmetic, in the
-// same per-thread order (so its sums are bit-identical to pass A's), with fewer shared-memory wavefronts AND fewer
-// instructions per particle:
+// kick_reduce_kernel<KICK_NONE> ran it at 0.39 of the copy roofline.  This kernel does the same arithmetic in the same
+// per-thread order (its sums are bit-identical to pass A's while every tile has a block of its own) with fewer
+// instructions and fewer shared-memory wavefronts per particle:
 //   - nothing is re-published: the molecule phase reads (vx, vy, vz, w) straight from the TMA stage and recomputes the
 //     mass (rcpMass: 5 instructions);
 //   - the pair phase needs only mu|v1 - v2|^2 (see passAPhase1): the Drude's lane reads its partner from the stage;
 //   - with nothing written to shared memory there is NO block barrier: every warp goes from the stage's `full` barrier to
-//     its `empty` arrival on its own.
+//     its `empty` arrival on its own, the warps of a block slip against each other by what the ring allows;
+//   - warps whose lanes hold none of the tile's molecules leave the molecule phase before its shuffles, and the molecule
+//     lanes rotate from tile to tile (below).
+// What its time follows is the number of warp instructions issued (ncu source page, profiles/ncu_r02_reduce_summary.txt:
+// ~2,600 per tile, issue slots 63 % busy with 27 warps per SM, fp64 pipe 48 %, DRAM 54 %): rewrites that relieved the
+// shared-memory pipe (bank-conflict-free half-swapped slot loads: data-pipe utilisation 77 -> 48 %) or the dependent
+// chains (straight-line code, two particles per round) but issued more instructions were all slower -- DESIGN.md 8.6c.
 // Cosine runs (which also need cos(kz) per particle, published once) keep the general kernel.
 template <int MODE> struct StageRed {
     typename Prec<MODE>::mixed4 velm[PADT];
@@ -845,9 +848,11 @@ template <int MODE> constexpr size_t smemBytesRed(int stages) {
 #ifndef ROT_RED
 #define ROT_RED (CTHREADS / 2)      // rotation of the molecule lanes from one tile of a block to the next (0: none)
 #endif
+// 3 blocks x 3 stages at 72 registers (no spills in the tile loop): with the rotated molecule lanes the deeper ring -- the
+// warps slip further against each other -- is worth more than a fourth block at 56 registers: 137 -> 128 us at 16.4M
 #ifndef MINBLOCKS_RED
-#define MINBLOCKS_RED 3       // 3 blocks x 3 stages, no spills: with the rotated molecule lanes the deeper ring (the warps
-#endif                        // slip further against each other) is worth more than a fourth block -- 137 -> 128 us
+#define MINBLOCKS_RED 3
+#endif
 
 
 template <int MODE>
