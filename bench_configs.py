@@ -105,7 +105,7 @@ def main():
 
         # the flow used when OpenMM constraints sit between the sub-steps (both example scripts use HBonds):
         # kick | thermostat_delta | finish = 440 B/particle (mixed); OpenMM's own solver launches are not included
-        split_us = None
+        split_us = split_graph_us = None
         if params.use_middle_scheme:
             pb = vv.Plan(spec, params, mode).upload()
             sb = vv.DeviceBuffers(host, with_pos_delta=True)
@@ -126,6 +126,28 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             split_us = 1e3 * e0.elapsed_time(e1) / (req_steps - 5)
+            # ... and replayed from a CUDA graph: three Python / ctypes calls per step cost the host more than the three
+            # kernels cost the GPU at these sizes, so the eager figure above is largely the harness's launch rate
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(stream)
+                with torch.cuda.stream(side):
+                    run_split(2)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        run_split(10)
+                    for _ in range(3):
+                        g.replay()
+                    side.synchronize()
+                    e0.record(side)
+                    for _ in range(max(1, req_steps // 10)):
+                        g.replay()
+                    e1.record(side)
+                    side.synchronize()
+                split_graph_us = 1e3 * e0.elapsed_time(e1) / (10 * max(1, req_steps // 10))
+                del g
+            except Exception as e:  # noqa: BLE001
+                split_graph_us = f"capture failed: {e}"
             del pb, sb
 
         ref_us = ref_launches = None
@@ -146,6 +168,7 @@ def main():
         row = {"config": name, "particles": spec.n, "precision": mode, "ours_us_per_step": ours_us,
                "ours_launches_per_step": launches, "ours_cuda_graph_us_per_step": graph_us,
                "ours_constrained_flow_us_per_step": split_us,
+               "ours_constrained_flow_cuda_graph_us_per_step": split_graph_us,
                "reference_kernels_us_per_step": ref_us, "reference_launches_per_step": ref_launches,
                "speedup_vs_reference_kernels": (ref_us / ours_us) if ref_us else None,
                "particle_updates_per_s": spec.n / (ours_us * 1e-6), "finite": finite}
