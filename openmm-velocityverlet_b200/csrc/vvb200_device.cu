@@ -203,6 +203,8 @@ struct KParams {
     double dt;
     double efscale, accel, invBoxZ, maxDrudeDistance, hardwallScale;
     int useCOM, hasLD, hasField, hardwall, extraForces, fuseNHC, cosine, kickOnly;
+    double maxD2safeD;                         // conservative pre-test of the hard wall: maxDrudeDistance^2 (1 - 1e-4), and as
+    float maxD2safeF;                          // the float the single / mixed kernels compare with
     int stagesA, stagesB;
     // single-launch resident kernel (vvb200_resident.cuh)
     int tilesPerBlock, doReduce;
@@ -1185,6 +1187,8 @@ static KParams makeParams(const vvb200_plan *p, const vvb200_buffers *b, const v
     k.invBoxZ = a ? a->inv_box_z : 0.0;
     k.maxDrudeDistance = p->par.max_drude_distance;          // :189
     k.hardwallScale = std::sqrt(BOLTZ_D * p->par.drude_temperature);   // :190
+    k.maxD2safeD = p->par.max_drude_distance * p->par.max_drude_distance * (1.0 - 1e-4);
+    k.maxD2safeF = (float) k.maxD2safeD;
     k.useCOM = p->par.use_com_temp_group != 0 && !p->moleculesNH.empty();
     k.hasLD = !p->particlesLD.empty();
     k.hasField = !p->particlesElectrolyte.empty();

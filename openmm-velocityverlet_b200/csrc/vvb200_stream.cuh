@@ -1077,13 +1077,18 @@ template <int MODE> struct BCtx {
     typedef typename Prec<MODE>::real real;
     typedef typename Prec<MODE>::mixed mixed;
     mixed stepSize, halfdt, invStepSize, fscaleVV, sA, sC, sD, Vb, maxD, hwScale;
-    real maxD2safe, efscale, accel, invBoxZ;
+    real efscale, accel, invBoxZ;
     bool cosine, useCOM;
     bool writeAllVel;   // resident kernel: pass A's kick is still in shared memory, every massive particle is written
 };
 
 // `nhc` values are read through L2 (__ldcg): in the resident kernel another block wrote them during this launch
 // `fac`: the factors as pass B's producer received them (hand-over); nullptr: from the thermostat state
+// conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold (KParams::maxD2safe*)
+template <class real> __device__ __forceinline__ real hardwallPretest(const KParams &p);
+template <> __device__ __forceinline__ float hardwallPretest<float>(const KParams &p) { return p.maxD2safeF; }
+template <> __device__ __forceinline__ double hardwallPretest<double>(const KParams &p) { return p.maxD2safeD; }
+
 template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams &p, bool extra, const double *fac = nullptr) {
     typedef typename Prec<MODE>::real real;
     typedef typename Prec<MODE>::mixed mixed;
@@ -1107,8 +1112,6 @@ template <int MODE> __device__ __forceinline__ BCtx<MODE> makeBCtx(const KParams
         c.Vb = c.cosine ? (mixed) __ldcg(&p.nhc->vBias) : (mixed) 0;
     }
     c.maxD = (mixed) p.maxDrudeDistance;
-    // conservative pre-test of the hard wall: below this squared distance `rInv*maxD < 1` cannot hold
-    c.maxD2safe = (real) (p.maxDrudeDistance * p.maxDrudeDistance * (1.0 - 1e-4));
     c.hwScale = (mixed) p.hardwallScale;
     c.efscale = (real) p.efscale;
     c.accel = (real) p.accel;
@@ -1134,7 +1137,9 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
     const real3 *ldForce = reinterpret_cast<const real3 *>(p.ldForce);
     const mixed stepSize = cx.stepSize, halfdt = cx.halfdt, invStepSize = cx.invStepSize, fscaleVV = cx.fscaleVV;
     const mixed sA = cx.sA, sC = cx.sC, sD = cx.sD, Vb = cx.Vb, maxD = cx.maxD, hwScale = cx.hwScale;
-    const real maxD2safe = cx.maxD2safe, efscale = cx.efscale, accel = cx.accel, invBoxZ = cx.invBoxZ;
+    // (the hard wall's pre-test threshold is read from the parameter block where it is used: a constant-bank operand, not
+    // one more loop-invariant register -- the velocity-Verlet variant spilled it and reloaded it once per tile and warp)
+    const real efscale = cx.efscale, accel = cx.accel, invBoxZ = cx.invBoxZ;
     const bool cosine = cx.cosine, useCOM = cx.useCOM;
     (void) posq; (void) corr; (void) ldForce; (void) invStepSize; (void) fscaleVV; (void) efscale; (void) accel;
     const int t0 = st.desc[0], t1 = st.desc[1], cbOff = st.desc[5];
@@ -1384,7 +1389,7 @@ __device__ __forceinline__ void passBTile(const KParams &p, const BCtx<MODE> &cx
             const real sx = (pq.x - pqq.x) + (cs.x - cqr.x) + (real) (ds[0] - dq[0]);
             const real sy = (pq.y - pqq.y) + (cs.y - cqr.y) + (real) (ds[1] - dq[1]);
             const real sz = (pq.z - pqq.z) + (cs.z - cqr.z) + (real) (ds[2] - dq[2]);
-            if (!(sx * sx + sy * sy + sz * sz < maxD2safe)) {
+            if (!(sx * sx + sy * sy + sz * sz < hardwallPretest<real>(p))) {
                 mixed xq[3] = {pqq.x + (mixed) cqr.x, pqq.y + (mixed) cqr.y, pqq.z + (mixed) cqr.z};
 #pragma unroll
                 for (int d = 0; d < 3; d++) xq[d] += dq[d];
@@ -1654,7 +1659,9 @@ __global__ void __launch_bounds__(passBConsumers(VARIANT) + 32, passBMinBlocks(V
     }
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = p.tileBegin + blockIdx.x; handOver || tile < p.tileEnd; tile += gridDim.x) {
+    // tiles this block takes under the static stride; under the hand-over the producer's end mark ends the loop
+    const int mine = p.tileEnd - p.tileBegin - (int) blockIdx.x;
+    for (int left = handOver ? 0x7fffffff : (mine > 0 ? (mine + (int) gridDim.x - 1) / (int) gridDim.x : 0); left > 0; left--) {
         mbarWait(full + s, phase);
         Stage &st = *reinterpret_cast<Stage *>(smemRaw + stageBytes * s);
 #ifdef VVB200_TRACE
