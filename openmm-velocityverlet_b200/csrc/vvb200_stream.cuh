@@ -854,7 +854,6 @@ template <int MODE> constexpr size_t smemBytesRed(int stages) {
 #define MINBLOCKS_RED 3
 #endif
 
-
 template <int MODE>
 __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const KParams p) {
     typedef Prec<MODE> P;
@@ -944,8 +943,10 @@ __global__ void __launch_bounds__(BTHREADS, MINBLOCKS_RED) reduce_kernel(const K
         // ahead by what the ring allows and then spin on a `full` barrier.  No barrier separates the tiles here, so the
         // molecule lanes ROTATE by half a block with every tile a block takes and each warp is the heavy one every other
         // tile.  (The block's first tile is unrotated: a system of one tile per block -- every bitwise fused-vs-split
-        // test -- sums in pass A's thread order; with several tiles per block the two kernels' per-block sums group the
-        // tiles differently anyway: 444 vs 444-592 blocks.)
+        // test -- sums in pass A's thread order.  With several tiles per block the molecule terms of every other tile reach
+        // the block's sum through other threads than in pass A: the group energies then agree to rounding, <= 1e-15
+        // relative; the scale factors are exp() of something 1e-5 small and do not see it -- split and fused trajectories
+        // of a 1M-particle box were still bit-identical after three steps.)
         if (nMol > 0) {
             const int rtid = (tid + rot) & (CTHREADS - 1);
             const int grp = rtid / COM_LANES, sub = rtid % COM_LANES;
